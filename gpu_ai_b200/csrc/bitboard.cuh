@@ -1,0 +1,371 @@
+// gpu_ai_b200/csrc/bitboard.cuh
+//
+// Checkers rules of krame505/gpu_ai on a packed 32-square bitboard, written for sm_100a
+// registers: every function is branch-light shift/mask arithmetic on 32-bit words, no local
+// arrays, no recursion.  Replaces the reference's 776-byte AoS State and its recursive
+// generators (reference: src/state.hpp:119-250, src/state.cu:57-92,122-180,239-340,388-420).
+//
+// Geometry (same numbering as the reference's own parallel generator, src/state.cu:185-188):
+//   square i = row*4 + col/2 ; dark squares only: row even -> cols 1,3,5,7, row odd -> 0,2,4,6.
+//   PLAYER_1 starts on rows 0-2 (bits 0-11) and moves toward row 7; PLAYER_2 the other way.
+//
+// Mover-normalised frame: all rule code below assumes "the side to move moves UP (toward
+// row 7)".  When PLAYER_2 is to move the three words are bit-reversed (180-degree board
+// rotation, i -> 31-i, one BREV each).  Under that rotation the reference's canonical move
+// list (squares row-major, then its per-square generator order, then DFS order) is exactly
+// REVERSED, because every direction order in the reference -- direct (+1,+1),(+1,-1),(-1,+1),
+// (-1,-1) (src/state.cu:257-258), man capture left-then-right (src/state.cu:326-337), king
+// capture (+1,+1),(+1,-1),(-1,+1),(-1,-1) (src/state.cu:391-392) -- is mapped onto its own
+// reverse.  So canonical index k of PLAYER_2 = index n-1-k in the normalised frame.
+//
+// The B2P_HD macro lets tests/host_build compile this header with g++ to unit-test the bit
+// logic on CPU against the oracle; the shipped library only uses the __device__ build.
+#pragma once
+
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define B2P_HD __host__ __device__ __forceinline__
+#else
+#define B2P_HD inline
+#endif
+
+namespace b2p {
+
+// ---- portable bit primitives ------------------------------------------------------------
+B2P_HD int popc(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+  return __popc(x);
+#else
+  return __builtin_popcount(x);
+#endif
+}
+B2P_HD uint32_t brev(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+  return __brev(x);
+#else
+  x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+  x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
+  x = ((x >> 4) & 0x0F0F0F0Fu) | ((x & 0x0F0F0F0Fu) << 4);
+  return __builtin_bswap32(x);
+#endif
+}
+// index of the lowest set bit (x != 0)
+B2P_HD int lowbit(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+  return __ffs((int)x) - 1;
+#else
+  return __builtin_ctz(x);
+#endif
+}
+B2P_HD uint32_t mulhi(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+  return __umulhi(a, b);
+#else
+  return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+
+// ---- one diagonal step, as a set image ------------------------------------------------------
+// direction codes: 0 = UR (+1,+1)  1 = UL (+1,-1)  2 = DR (-1,+1)  3 = DL (-1,-1)
+// From an even row: UL=i+4 UR=i+5 DL=i-4 DR=i-3 ; from an odd row: UL=i+3 UR=i+4 DL=i-5 DR=i-4.
+// Masks drop the squares that would leave the board sideways (col 7 going right = even-row
+// bits with i%4==3; col 0 going left = odd-row bits with i%4==0); rows fall off the word.
+constexpr uint32_t kEvenRows = 0x0F0F0F0Fu;
+constexpr uint32_t kOddRows = 0xF0F0F0F0u;
+constexpr uint32_t kEvenNotCol7 = 0x07070707u;
+constexpr uint32_t kOddNotCol0 = 0xE0E0E0E0u;
+
+B2P_HD uint32_t stepUR(uint32_t x) { return ((x & kEvenNotCol7) << 5) | ((x & kOddRows) << 4); }
+B2P_HD uint32_t stepUL(uint32_t x) { return ((x & kEvenRows) << 4) | ((x & kOddNotCol0) << 3); }
+B2P_HD uint32_t stepDR(uint32_t x) { return ((x & kEvenNotCol7) >> 3) | ((x & kOddRows) >> 4); }
+B2P_HD uint32_t stepDL(uint32_t x) { return ((x & kEvenRows) >> 4) | ((x & kOddNotCol0) >> 5); }
+
+// two steps in one direction (a jump landing): +9 / +7 / -7 / -9, legal while col+-2 stays on
+// the board (i%4 <= 2 going right, i%4 >= 1 going left)
+constexpr uint32_t kNotRight2 = 0x77777777u;
+constexpr uint32_t kNotLeft2 = 0xEEEEEEEEu;
+B2P_HD uint32_t jumpUR(uint32_t x) { return (x & kNotRight2) << 9; }
+B2P_HD uint32_t jumpUL(uint32_t x) { return (x & kNotLeft2) << 7; }
+B2P_HD uint32_t jumpDR(uint32_t x) { return (x & kNotRight2) >> 7; }
+B2P_HD uint32_t jumpDL(uint32_t x) { return (x & kNotLeft2) >> 9; }
+
+// per-square scalars: target index of one step / one jump from square s in direction d
+B2P_HD int step_target(int s, int d) {
+  // {+5,+4,-3,-4} on even rows, one less on odd rows
+  const int base = (int)((0xFCFD0405u >> (8 * d)) & 0xFF);  // bytes: 5, 4, -3, -4 (two's complement)
+  return s + (int)(int8_t)base - ((s >> 2) & 1);
+}
+B2P_HD int jump_target(int s, int d) {
+  const int base = (int)((0xF7F90709u >> (8 * d)) & 0xFF);  // bytes: 9, 7, -7, -9
+  return s + (int)(int8_t)base;
+}
+
+// ---- position in the mover-normalised frame -----------------------------------------------
+struct Pos {
+  uint32_t own;    // pieces of the side to move
+  uint32_t opp;    // pieces of the other side
+  uint32_t kings;  // kings of both sides
+};
+
+// jump availability per direction, independent of what stands on the origin square:
+// J[d] bit s set <=> the square one step from s in direction d holds an enemy and the square
+// two steps away is empty.  The reference never modifies the board while it extends a
+// capture sequence (src/state.cu:129-131 test the original board), so these four masks are
+// valid for EVERY hop of every sequence of the ply.
+struct JumpMasks {
+  uint32_t j[4];
+};
+
+B2P_HD JumpMasks jump_masks(const Pos &p) {
+  const uint32_t empty = ~(p.own | p.opp);
+  JumpMasks m;
+  m.j[0] = stepDL(p.opp & stepDL(empty));  // s --UR--> enemy --UR--> empty
+  m.j[1] = stepDR(p.opp & stepDR(empty));
+  m.j[2] = stepUL(p.opp & stepUL(empty));
+  m.j[3] = stepUR(p.opp & stepUR(empty));
+  return m;
+}
+
+// squares of the mover that have a first hop, per direction (men: up only)
+B2P_HD void capture_origins(const Pos &p, const JumpMasks &m, uint32_t out[4]) {
+  const uint32_t ownK = p.own & p.kings;
+  out[0] = p.own & m.j[0];
+  out[1] = p.own & m.j[1];
+  out[2] = ownK & m.j[2];
+  out[3] = ownK & m.j[3];
+}
+
+// squares of the mover that have a direct move, per direction (reference: genLocDirectMoves,
+// src/state.cu:255-281)
+B2P_HD void step_origins(const Pos &p, uint32_t out[4]) {
+  const uint32_t empty = ~(p.own | p.opp);
+  const uint32_t ownK = p.own & p.kings;
+  out[0] = p.own & stepDL(empty);
+  out[1] = p.own & stepDR(empty);
+  out[2] = ownK & stepUL(empty);
+  out[3] = ownK & stepUR(empty);
+}
+
+// true if some capture can be extended by a second hop (then the move list is not just
+// "one entry per first hop" and the DFS below is needed)
+B2P_HD bool any_second_hop(const Pos &p, const JumpMasks &m, const uint32_t cap[4]) {
+  const uint32_t men = ~p.kings;
+  const uint32_t land_men = jumpUR(cap[0] & men) | jumpUL(cap[1] & men);
+  const uint32_t land_king = jumpUR(cap[0] & p.kings) | jumpUL(cap[1] & p.kings) | jumpDR(cap[2]) | jumpDL(cap[3]);
+  const uint32_t up = m.j[0] | m.j[1];
+  return ((land_men & up) | (land_king & (up | m.j[2] | m.j[3]))) != 0;
+}
+
+// ---- applying a move ----------------------------------------------------------------------
+// reference: State::move, src/state.cu:57-92.  `from`/`to` are single-bit masks, `captured`
+// the set of jumped squares (empty for a direct move).  A man that ends on row 7 (bits 28-31
+// of the normalised frame) is crowned: direct moves src/state.cu:274-276, captures :315-320.
+B2P_HD void apply_move(Pos &p, uint32_t from, uint32_t to, uint32_t captured) {
+  const uint32_t was_king = p.kings & from;
+  p.own ^= from | to;
+  p.opp &= ~captured;
+  p.kings &= ~(captured | from);
+  if (was_king | (to & 0xF0000000u)) p.kings |= to;
+}
+
+// hand the move to the other side: rotate the board by 180 degrees
+B2P_HD Pos flip(const Pos &p) {
+  Pos q;
+  q.own = brev(p.opp);
+  q.opp = brev(p.own);
+  q.kings = brev(p.kings);
+  return q;
+}
+
+// ---- selecting the k-th set bit ---------------------------------------------------------------
+B2P_HD int select_bit(uint32_t m, int k) {
+  int r = 0, c;
+  c = popc(m & 0xFFFFu); if (k >= c) { k -= c; m >>= 16; r = 16; }
+  c = popc(m & 0xFFu);   if (k >= c) { k -= c; m >>= 8;  r += 8; }
+  c = popc(m & 0xFu);    if (k >= c) { k -= c; m >>= 4;  r += 4; }
+  c = popc(m & 0x3u);    if (k >= c) { k -= c; m >>= 2;  r += 2; }
+  c = (int)(m & 1u);     if (k >= c) { r += 1; }
+  return r;
+}
+
+// Order of the (origin, slot) pairs of four origin masks a[0..3]:
+//   kOrderFast      direction-major: all of a[0] by ascending origin, then a[1], ...
+//   kOrderCanonical origin-major   : ascending origin, then slot 0..3 -- the reference's list
+//                                    order in the normalised frame
+// Returns origin | slot << 5 for rank k (0 <= k < total).
+enum { kOrderCanonical = 0, kOrderFast = 1 };
+
+B2P_HD int select_dir_major(const uint32_t a[4], int n0, int n1, int n2, int k) {
+  int slot = 0;
+  uint32_t m = a[0];
+  if (k >= n0) { k -= n0; m = a[1]; slot = 1;
+    if (k >= n1) { k -= n1; m = a[2]; slot = 2;
+      if (k >= n2) { k -= n2; m = a[3]; slot = 3; } } }
+  return select_bit(m, k) | (slot << 5);
+}
+
+B2P_HD int select_origin_major(const uint32_t a[4], int k) {
+  // binary search for the origin o with  count(origins < o) <= k < count(origins <= o)
+  int lo = 0, below = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int w = 16; w >= 1; w >>= 1) {
+    const uint32_t lm = (1u << (lo + w)) - 1u;
+    const int c = popc(a[0] & lm) + popc(a[1] & lm) + popc(a[2] & lm) + popc(a[3] & lm);
+    if (c <= k) { lo += w; below = c; }
+  }
+  int r = k - below;  // rank among the slots present at origin lo
+  const uint32_t nib = ((a[0] >> lo) & 1u) | (((a[1] >> lo) & 1u) << 1) | (((a[2] >> lo) & 1u) << 2) | (((a[3] >> lo) & 1u) << 3);
+  // r-th set bit of a 4-bit value
+  uint32_t t = nib;
+  if (r >= 1) t &= t - 1;
+  if (r >= 2) t &= t - 1;
+  if (r >= 3) t &= t - 1;
+  return lo | (lowbit(t) << 5);
+}
+
+// ---- capture sequences: iterative DFS over the static jump graph -----------------------------
+// Enumerates every complete capture sequence in the normalised canonical order: origins
+// ascending; men try UL then UR (reference: left before right, src/state.cu:326-337), kings
+// UR, UL, DR, DL with "landing square not landed on before" (src/state.cu:134-139); a
+// sequence is complete when no hop is possible (src/state.cu:314-322, :403-409).
+// The whole DFS state lives in six registers: per-depth "next slot" counters (3 bits each),
+// the landing path (5 bits each), visited and captured masks.
+struct CaptureMove {
+  int from, to, hops;
+  uint32_t captured;  // jumped squares
+  uint64_t path;      // landing square of hop k in bits [5k, 5k+5)
+};
+
+// Calls visit(const CaptureMove&) for sequence number 0,1,2,...; visit returns true to stop.
+// Returns the number of sequences visited.
+template <class Visit>
+B2P_HD int for_each_capture(const Pos &p, const JumpMasks &m, Visit &&visit) {
+  uint32_t cap[4];
+  capture_origins(p, m, cap);
+  uint32_t origins = cap[0] | cap[1] | cap[2] | cap[3];
+  int count = 0;
+  while (origins) {
+    const int o = lowbit(origins);
+    origins &= origins - 1;
+    const bool king = (p.kings >> o) & 1u;
+    int cur = o, depth = 0;
+    uint32_t next = 0;       // next slot to try at each depth
+    uint32_t visited = 0;    // landing squares of the current sequence
+    uint32_t captured = 0;
+    uint64_t path = 0;
+    for (;;) {
+      // slots that can be hopped from `cur` (slot order = reference order for this piece type)
+      uint32_t v;
+      if (king) {
+        v = 0;
+        for (int d = 0; d < 4; d++) {
+          const int land = jump_target(cur, d);
+          const uint32_t ok = (m.j[d] >> cur) & 1u;
+          // land may be out of range when ok == 0; guard the shift
+          const uint32_t seen = ok ? ((visited >> (land & 31)) & 1u) : 0u;
+          v |= (ok & ~seen) << d;
+        }
+      } else {
+        v = ((m.j[1] >> cur) & 1u) | (((m.j[0] >> cur) & 1u) << 1);
+      }
+      const int ns = (int)((next >> (3 * depth)) & 7u);
+      const uint32_t todo = v & (0xFu << ns);
+      if (todo == 0) {
+        if (v == 0 && depth > 0) {
+          CaptureMove cm;
+          cm.from = o; cm.to = cur; cm.hops = depth; cm.captured = captured; cm.path = path;
+          count++;
+          if (visit(cm)) return count;
+        }
+        if (depth == 0) break;
+        // pop: undo the hop that led to `cur`
+        depth--;
+        const int slot = (int)((next >> (3 * depth)) & 7u) - 1;
+        const int d = king ? slot : (slot ^ 1);
+        const int parent = cur - (jump_target(cur, d) - cur);
+        visited &= ~(1u << cur);
+        captured &= ~(1u << step_target(parent, d));
+        path &= ~((uint64_t)31 << (5 * depth));
+        cur = parent;
+      } else {
+        const int slot = lowbit(todo);
+        const int d = king ? slot : (slot ^ 1);
+        next = (next & ~(7u << (3 * depth))) | ((uint32_t)(slot + 1) << (3 * depth));
+        const int land = jump_target(cur, d);
+        captured |= 1u << step_target(cur, d);
+        visited |= 1u << land;
+        path |= (uint64_t)land << (5 * depth);
+        depth++;
+        next &= ~(7u << (3 * depth));
+        cur = land;
+      }
+    }
+  }
+  return count;
+}
+
+// ---- material (heuristic) -----------------------------------------------------------------
+// reference: pieceValue / scoreState, src/heuristic.cu:7-31 (man 1, king 4)
+B2P_HD uint32_t material(uint32_t pieces, uint32_t kings) { return (uint32_t)(popc(pieces) + 3 * popc(pieces & kings)); }
+
+// ---- the 64-bit move record of b2p_genmoves (include/b2p.h) -----------------------------------
+B2P_HD uint64_t encode_move(int from, int to, int hops, bool promoted, uint64_t path) {
+  return (uint64_t)from | ((uint64_t)to << 5) | ((uint64_t)hops << 10) | ((uint64_t)(promoted ? 1 : 0) << 13) | (path << 16);
+}
+
+// Writes the reference-canonical move list (absolute frame, reference order) of a packed
+// state; returns the number of legal moves (may exceed max_out; only max_out are stored).
+// reference: State::genMoves, src/state.cu:239-245.
+B2P_HD int gen_moves_canonical(uint32_t p1, uint32_t p2, uint32_t kings, uint32_t turn, uint64_t *out, int max_out) {
+  Pos p;
+  if (turn == 0) { p.own = p1; p.opp = p2; p.kings = kings; }
+  else { p.own = brev(p2); p.opp = brev(p1); p.kings = brev(kings); }
+  const JumpMasks jm = jump_masks(p);
+  const uint32_t ownMen = p.own & ~p.kings;
+  // pass 1: count (needed because PLAYER_2's list is the normalised list reversed)
+  uint32_t cap[4];
+  capture_origins(p, jm, cap);
+  int n;
+  const bool capture = (cap[0] | cap[1] | cap[2] | cap[3]) != 0;
+  uint32_t st[4];
+  if (capture) {
+    n = for_each_capture(p, jm, [](const CaptureMove &) { return false; });
+  } else {
+    step_origins(p, st);
+    n = popc(st[0]) + popc(st[1]) + popc(st[2]) + popc(st[3]);
+  }
+  // pass 2: emit
+  auto put = [&](int idx_norm, int from, int to, int hops, bool promoted, uint64_t path) {
+    int idx = idx_norm;
+    if (turn != 0) {
+      idx = n - 1 - idx_norm;
+      from = 31 - from; to = 31 - to;
+      uint64_t q = 0;
+      for (int k = 0; k < hops; k++) q |= (uint64_t)(31 - (int)((path >> (5 * k)) & 31)) << (5 * k);
+      path = q;
+    }
+    if (idx < max_out) out[idx] = encode_move(from, to, hops, promoted, path);
+  };
+  if (capture) {
+    int i = 0;
+    for_each_capture(p, jm, [&](const CaptureMove &cm) {
+      const bool promoted = ((ownMen >> cm.from) & 1u) && cm.to >= 28;
+      put(i++, cm.from, cm.to, cm.hops, promoted, cm.path);
+      return false;
+    });
+  } else {
+    for (int k = 0; k < n; k++) {
+      const int sel = select_origin_major(st, k);
+      const int o = sel & 31, d = sel >> 5;
+      const int to = step_target(o, d);
+      const bool promoted = ((ownMen >> o) & 1u) && to >= 28;
+      put(k, o, to, 0, promoted, 0);
+    }
+  }
+  return n;
+}
+
+}  // namespace b2p

@@ -1,0 +1,256 @@
+// gpu_ai_b200/csrc/kernels.cu -- hand-written sm_100a kernels of the playout hot path.
+//
+// Replaces singlePlayoutKernel (src/singlePlayout.cu:16-69), playoutKernel
+// (src/multiplePlayout.cu:14-51), coarsePlayoutKernel (src/coarsePlayout.cu:18-89),
+// heuristicPlayoutKernel (src/heuristicPlayout.cu:16-100) and genMovesKernel
+// (src/genMovesTest.cu:10-24) of the reference.
+//
+// Design (DESIGN.md has the full account):
+//  * a playout lives entirely in registers: 3 board words, turn, draw counter, ply counter;
+//    no local memory, no shared memory on the random path, no recursion, no device stack.
+//  * persistent lanes: every lane of every resident warp owns one playout at a time; finished
+//    lanes are refilled together, once every 4 plies, with ONE warp-aggregated atomicAdd on the
+//    work-queue head (__ballot_sync + __popc prefix) -- the same point where all lanes draw their
+//    next Philox4x32-10 block, so both the refill and the RNG run converged.
+//  * the only global traffic is one coalesced LDG.128 per playout and one STG.8 per result.
+//  * integer work only (LOP3 / SHF / IADD3 / POPC / IMAD); no tensor cores: nothing here is a
+//    contraction.
+#include "kernels.cuh"
+
+#include "bitboard.cuh"
+#define B2P_GAUSS_QUAL __device__ const
+#include "gauss_table_bits.h"
+#include "philox.cuh"
+#include "playout_core.cuh"
+
+namespace b2p {
+
+namespace {
+
+constexpr int kLaneBlock = 128;
+constexpr unsigned kFull = 0xFFFFFFFFu;
+
+__device__ __forceinline__ uint32_t pick4(const Philox4 &b, int q) {
+  uint32_t r = b.v[0];
+  r = q == 1 ? b.v[1] : r;
+  r = q == 2 ? b.v[2] : r;
+  r = q == 3 ? b.v[3] : r;
+  return r;
+}
+
+__device__ __forceinline__ float gauss_lookup(const float *tab, uint32_t r) {
+  const uint32_t i = r >> 22;
+  const float frac = (float)(r & 0x3FFFFFu) * (1.0f / 4194304.0f);
+  const float lo = tab[i], hi = tab[i + 1];
+  return __fmaf_rn(hi - lo, frac, lo);
+}
+
+// ---------------------------------------------------------------------------------------------
+// thread-per-playout, persistent lanes
+// ---------------------------------------------------------------------------------------------
+template <int MODE, bool LIMITED>
+__global__ void __launch_bounds__(kLaneBlock) playout_lanes_kernel(const PlayoutParams prm) {
+  constexpr bool kHeur = MODE == kHeuristic;
+  constexpr bool kLeaf = MODE == kLeafGen;
+  constexpr int kOrder = MODE == kRandomFast ? kOrderFast : kOrderCanonical;
+  constexpr uint32_t kDomain = kLeaf ? kDomainLeaf : kDomainRandom;
+
+  __shared__ float s_gauss[kHeur ? 1025 : 1];
+  if (kHeur) {
+    for (int i = threadIdx.x; i < 1025; i += blockDim.x) s_gauss[i] = __uint_as_float(b2p_gauss_table_bits[i]);
+    __syncthreads();
+  }
+
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned below = (1u << lane) - 1u;
+
+  Game g;
+  g.pos.own = g.pos.opp = g.pos.kings = 0;
+  g.turn = g.msc = 0;
+  uint32_t w = 0, ply = 0, blk = 0;
+  uint64_t pid = 0;
+  int limit = prm.max_plies;
+  bool busy = false;
+  bool more = true;  // warp-uniform: the queue may still hold work
+  uint32_t c_none = 0, c_p1 = 0, c_p2 = 0, c_plies = 0;
+
+  for (;;) {
+    // ---- refill: all idle lanes of the warp take consecutive work items --------------------
+    const unsigned idle = __ballot_sync(kFull, !busy);
+    if (idle != 0u && more) {
+      const uint32_t cnt = (uint32_t)__popc(idle);
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(prm.next, cnt);
+      base = __shfl_sync(kFull, base, 0);
+      more = base + cnt < prm.total;
+      if (!busy) {
+        w = base + (uint32_t)__popc(idle & below);
+        if (w < prm.total) {
+          uint32_t leaf = w, rep = 0;
+          if (prm.total != prm.n) {
+            rep = w / prm.n;
+            leaf = w - rep * prm.n;
+          }
+          pid = prm.pid_base + (uint64_t)rep * prm.rep_stride + leaf;
+          if (kLeaf) {
+            g = load_game(0x00000FFFu, 0xFFF00000u, 0u, 0u);  // getStartingState, src/state.cpp:25-40
+          } else {
+            const uint4 s = __ldg(prm.states + leaf);
+            g = load_game(s.x, s.y, s.z, s.w);
+          }
+          busy = true;
+          ply = 0;
+          blk = 0;
+          limit = prm.max_plies;
+        }
+      }
+    }
+    if (__ballot_sync(kFull, busy) == 0u) break;
+
+    // ---- one Philox block = the draws of the next 4 plies (converged across the warp) -------
+    Philox4 rnd;
+    if (!kHeur) rnd = philox_block(prm.key, pid, kDomain, blk);
+    blk++;
+
+#pragma unroll 1
+    for (int q = 0; q < 4; q++) {
+      if (!busy) continue;
+      int res = kRunning;
+      if (kLeaf && blk == 1 && q == 0) {
+        // draw 0 of the leaf stream: prefix length U{1..100} (src/driver.cpp:80,86)
+        limit = 1 + (int)mulhi(rnd.v[0], 100u);
+        continue;
+      }
+      if ((LIMITED || kLeaf) && limit >= 0 && (int)ply >= limit) {
+        // stopped by the ply limit: report the winner if the game happens to be over here
+        Game probe = g;
+        res = random_ply<kOrderFast>(probe, 0u);
+        if (res == kRunning) res = 3;  // marker: unfinished
+      } else if (kHeur) {
+        int cached = -1;
+        Philox4 nb;
+        nb.v[0] = nb.v[1] = nb.v[2] = nb.v[3] = 0;
+        res = heuristic_ply(g, [&](int i) {
+          const int b = i >> 2;
+          if (b != cached) {
+            nb = philox_block(prm.key, pid, kDomainNoise | ((uint32_t)b << 8), ply);
+            cached = b;
+          }
+          return gauss_lookup(s_gauss, pick4(nb, i & 3));
+        });
+      } else {
+        res = random_ply<kOrder>(g, pick4(rnd, q));
+      }
+      if (res == kRunning) {
+        ply++;
+        continue;
+      }
+      // ---- playout finished: publish --------------------------------------------------------
+      if (res == 3) res = kRunning;
+      if (prm.winners) prm.winners[w] = (int8_t)res;
+      if (LIMITED || kLeaf) {
+        if (prm.plies) prm.plies[w] = ply;
+        if (prm.final_states) {
+          uint32_t o[4];
+          store_game(g, o);
+          prm.final_states[w] = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+      }
+      c_none += res == -1;
+      c_p1 += res == 0;
+      c_p2 += res == 1;
+      c_plies += ply;
+      busy = false;
+    }
+  }
+
+  // ---- per-warp reduction of the win counters, one atomic per counter per warp ---------------
+  if (prm.counters) {
+    c_none = __reduce_add_sync(kFull, c_none);
+    c_p1 = __reduce_add_sync(kFull, c_p1);
+    c_p2 = __reduce_add_sync(kFull, c_p2);
+    unsigned long long pl = c_plies;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) pl += __shfl_xor_sync(kFull, pl, o);
+    if (lane == 0) {
+      if (c_none) atomicAdd(prm.counters + 0, (unsigned long long)c_none);
+      if (c_p1) atomicAdd(prm.counters + 1, (unsigned long long)c_p1);
+      if (c_p2) atomicAdd(prm.counters + 2, (unsigned long long)c_p2);
+      if (pl) atomicAdd(prm.counters + 3, pl);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// batched canonical move lists (parity kernel)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) genmoves_kernel(const uint4 *__restrict__ states, uint32_t n, int max_moves,
+                                                       unsigned long long *__restrict__ moves,
+                                                       uint8_t *__restrict__ counts) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint4 s = __ldg(states + i);
+  const int cnt = gen_moves_canonical(s.x, s.y, s.z & (s.x | s.y), s.w & 1u,
+                                      reinterpret_cast<uint64_t *>(moves) + (size_t)i * max_moves, max_moves);
+  counts[i] = (uint8_t)(cnt > 255 ? 255 : cnt);
+}
+
+template <int MODE, bool LIMITED>
+cudaError_t launch_lanes_t(const PlayoutParams &prm, int sm_count, cudaStream_t stream, LaunchInfo *info) {
+  auto kern = playout_lanes_kernel<MODE, LIMITED>;
+  int per_sm = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kLaneBlock, 0);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) per_sm = 1;
+  long long want = ((long long)prm.total + kLaneBlock - 1) / kLaneBlock;
+  long long cap = (long long)sm_count * per_sm;
+  int grid = (int)(want < cap ? want : cap);
+  if (grid < 1) grid = 1;
+  if (info) {
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, kern);
+    info->grid = grid;
+    info->block = kLaneBlock;
+    info->regs = fa.numRegs;
+    info->blocks_per_sm = per_sm;
+  }
+  e = cudaMemsetAsync(prm.next, 0, sizeof(unsigned int), stream);
+  if (e != cudaSuccess) return e;
+  kern<<<grid, kLaneBlock, 0, stream>>>(prm);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_playout_lanes(const PlayoutParams &prm, KernelMode mode, int sm_count, cudaStream_t stream,
+                                 LaunchInfo *info) {
+  const bool limited = prm.max_plies >= 0 || prm.plies != nullptr || prm.final_states != nullptr;
+  switch (mode) {
+    case kRandomCanonical:
+      return limited ? launch_lanes_t<kRandomCanonical, true>(prm, sm_count, stream, info)
+                     : launch_lanes_t<kRandomCanonical, false>(prm, sm_count, stream, info);
+    case kRandomFast:
+      return limited ? launch_lanes_t<kRandomFast, true>(prm, sm_count, stream, info)
+                     : launch_lanes_t<kRandomFast, false>(prm, sm_count, stream, info);
+    case kHeuristic:
+      return limited ? launch_lanes_t<kHeuristic, true>(prm, sm_count, stream, info)
+                     : launch_lanes_t<kHeuristic, false>(prm, sm_count, stream, info);
+    case kLeafGen:
+      return launch_lanes_t<kLeafGen, true>(prm, sm_count, stream, info);
+  }
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_playout_warp(const PlayoutParams &, KernelMode, int, cudaStream_t, LaunchInfo *) {
+  return cudaErrorNotSupported;  // warp-per-playout variant: see warp_kernel.cu (round 1: not built yet)
+}
+
+cudaError_t launch_genmoves(const uint4 *states, uint32_t n, int max_moves, unsigned long long *moves, uint8_t *counts,
+                            cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  const int block = 128;
+  genmoves_kernel<<<(n + block - 1) / block, block, 0, stream>>>(states, n, max_moves, moves, counts);
+  return cudaGetLastError();
+}
+
+}  // namespace b2p

@@ -1,0 +1,222 @@
+"""ctypes binding of include/b2p.h (libb2p.so).  Thin: argument marshalling and error mapping only."""
+import ctypes as C
+import os
+
+import numpy as np
+
+MODE_RANDOM, MODE_HEURISTIC = 0, 1
+SCHED_THREAD, SCHED_WARP, SCHED_AUTO = 0, 1, 2
+ORDER_CANONICAL, ORDER_FAST = 0, 1
+UNFINISHED = 2
+
+STATE776_BYTES = 776  # sizeof(State) of the reference (src/state.hpp:119-122)
+MOVE_BYTES = 38       # sizeof(Move)  of the reference (src/state.hpp:253-296)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class B2PError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return os.path.join(_HERE, "libb2p.so")
+
+
+class DevInfo(C.Structure):
+    _fields_ = [("device_id", C.c_int), ("sm_count", C.c_int), ("clock_khz", C.c_int), ("cc_major", C.c_int),
+                ("cc_minor", C.c_int), ("total_mem", C.c_size_t), ("name", C.c_char * 128)]
+
+
+# every symbol include/b2p.h declares: (name, restype, argtypes)
+_VP, _U64, _U32, _SZ, _INT = C.c_void_p, C.c_uint64, C.c_uint32, C.c_size_t, C.c_int
+ABI = [
+    ("b2p_create", _INT, [C.POINTER(_VP), C.POINTER(C.c_int), _INT, _U64]),
+    ("b2p_destroy", None, [_VP]),
+    ("b2p_last_error", C.c_char_p, [_VP]),
+    ("b2p_device_count", _INT, [_VP]),
+    ("b2p_device_info", _INT, [_VP, _INT, C.POINTER(DevInfo)]),
+    ("b2p_version", C.c_char_p, []),
+    ("b2p_run_states776", _INT, [_VP, _VP, _SZ, _INT, _INT, _VP]),
+    ("b2p_run_packed", _INT, [_VP, _VP, _SZ, _U32, _U64, _U64, _INT, _INT, _INT, _INT, _VP, _VP, _VP, _VP]),
+    ("b2p_genmoves", _INT, [_VP, _VP, _SZ, _INT, _VP, _VP]),
+    ("b2p_run_packed_device", _INT, [_VP, _INT, _VP, _SZ, _U32, _U64, _U64, _INT, _INT, _INT, _INT, _VP, _VP, _VP, _VP, _VP]),
+    ("b2p_genmoves_device", _INT, [_VP, _INT, _VP, _SZ, _INT, _VP, _VP, _VP]),
+    ("b2p_gen_leaves_device", _INT, [_VP, _INT, _SZ, _U64, _U64, _VP, _VP]),
+    ("b2p_gen_leaves", _INT, [_VP, _SZ, _U64, _U64, _VP]),
+    ("b2p_sync", _INT, [_VP]),
+    ("b2p_pack776", _INT, [_VP, _SZ, _VP]),
+    ("b2p_unpack776", _INT, [_VP, _SZ, _VP]),
+    ("b2p_expand_move", _INT, [_U64, _VP]),
+    ("b2p_microbench", _INT, [_VP, _INT, _INT, _INT, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    ("b2p_launch_count", _U64, [_VP]),
+]
+
+_lib = None
+
+
+def load_library():
+    """Load libb2p.so and bind every ABI symbol.  Fails loudly if the extension was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise B2PError("%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "or `make -C gpu_ai_b200/csrc`. There is no CPU fallback." % path)
+    lib = C.CDLL(path)
+    for name, res, args in ABI:
+        fn = getattr(lib, name)  # AttributeError here = header/library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _ptr(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def _as_packed(states):
+    a = np.ascontiguousarray(states, dtype=np.uint32)
+    if a.ndim == 1:
+        a = a.reshape(-1, 4)
+    if a.ndim != 2 or a.shape[1] != 4:
+        raise ValueError("packed states must have shape (n, 4) uint32")
+    return a
+
+
+class Engine:
+    """One b2p context (= the set of GPUs one playout driver uses)."""
+
+    def __init__(self, devices=None, seed=12345):
+        self.lib = load_library()
+        self.ctx = C.c_void_p()
+        if devices is None:
+            ids, n = None, 0
+        elif isinstance(devices, int):
+            ids, n = None, devices
+        else:
+            devices = list(devices)
+            ids, n = (C.c_int * len(devices))(*devices), len(devices)
+        rc = self.lib.b2p_create(C.byref(self.ctx), ids, n, seed)
+        if rc != 0:
+            msg = self.lib.b2p_last_error(None)
+            self.ctx = None
+            raise B2PError("b2p_create failed (%d): %s" % (rc, msg.decode() if msg else "?"))
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.b2p_destroy(self.ctx)
+            self.ctx = None
+
+    __del__ = close
+
+    def _check(self, rc):
+        if rc != 0:
+            raise B2PError("b2p error %d: %s" % (rc, self.lib.b2p_last_error(self.ctx).decode()))
+
+    # ---- info ----------------------------------------------------------------------------------
+    @property
+    def device_count(self):
+        return self.lib.b2p_device_count(self.ctx)
+
+    def device_info(self, i=0):
+        d = DevInfo()
+        self._check(self.lib.b2p_device_info(self.ctx, i, C.byref(d)))
+        return {"device_id": d.device_id, "sm_count": d.sm_count, "clock_khz": d.clock_khz,
+                "cc": (d.cc_major, d.cc_minor), "total_mem": d.total_mem, "name": d.name.decode()}
+
+    @property
+    def launch_count(self):
+        return int(self.lib.b2p_launch_count(self.ctx))
+
+    def sync(self):
+        self._check(self.lib.b2p_sync(self.ctx))
+
+    # ---- host-buffer calls ------------------------------------------------------------------------
+    def run_states776(self, states776, mode=MODE_RANDOM, sched=SCHED_THREAD, out=None):
+        """states776: bytes-like / uint8 array of n reference `State` objects.  Returns int32 PlayerId[n]."""
+        buf = np.ascontiguousarray(np.frombuffer(states776, dtype=np.uint8) if not isinstance(states776, np.ndarray) else states776, dtype=np.uint8).reshape(-1)
+        if buf.size % STATE776_BYTES:
+            raise ValueError("buffer is not a whole number of 776-byte States")
+        n = buf.size // STATE776_BYTES
+        if out is None:
+            out = np.empty(n, dtype=np.int32)
+        self._check(self.lib.b2p_run_states776(self.ctx, _ptr(buf), n, mode, sched, _ptr(out)))
+        return out
+
+    def run_packed(self, states, reps=1, key=12345, pid_base=0, mode=MODE_RANDOM, sched=SCHED_THREAD,
+                   order=ORDER_CANONICAL, max_plies=-1, want_winners=True, want_plies=False, want_final=False):
+        a = _as_packed(states)
+        n = a.shape[0]
+        total = n * reps
+        winners = np.empty(total, dtype=np.int8) if want_winners else None
+        plies = np.empty(total, dtype=np.uint32) if want_plies else None
+        final = np.empty((total, 4), dtype=np.uint32) if want_final else None
+        counters = np.zeros(4, dtype=np.uint64)
+        self._check(self.lib.b2p_run_packed(self.ctx, _ptr(a), n, reps, key, pid_base, mode, sched, order, max_plies,
+                                            _ptr(winners), _ptr(plies), _ptr(final), _ptr(counters)))
+        return winners, plies, final, counters
+
+    def genmoves(self, states, max_moves=64):
+        a = _as_packed(states)
+        n = a.shape[0]
+        moves = np.zeros((n, max_moves), dtype=np.uint64)
+        counts = np.zeros(n, dtype=np.uint8)
+        self._check(self.lib.b2p_genmoves(self.ctx, _ptr(a), n, max_moves, _ptr(moves), _ptr(counts)))
+        return moves, counts
+
+    def gen_leaves(self, n, key=2016, first_index=0):
+        out = np.empty((n, 4), dtype=np.uint32)
+        self._check(self.lib.b2p_gen_leaves(self.ctx, n, key, first_index, _ptr(out)))
+        return out
+
+    # ---- device-resident calls (raw device pointers, e.g. torch tensor.data_ptr()) ---------------------
+    def run_packed_device(self, d_states, n, reps=1, key=12345, pid_base=0, mode=MODE_RANDOM, sched=SCHED_THREAD,
+                          order=ORDER_FAST, max_plies=-1, d_winners=None, d_plies=None, d_final=None, d_counters=None,
+                          stream=None, dev_index=0):
+        self._check(self.lib.b2p_run_packed_device(self.ctx, dev_index, d_states, n, reps, key, pid_base, mode, sched,
+                                                   order, max_plies, d_winners, d_plies, d_final, d_counters, stream))
+
+    def genmoves_device(self, d_states, n, max_moves, d_moves, d_counts, stream=None, dev_index=0):
+        self._check(self.lib.b2p_genmoves_device(self.ctx, dev_index, d_states, n, max_moves, d_moves, d_counts, stream))
+
+    def gen_leaves_device(self, n, d_out, key=2016, first_index=0, stream=None, dev_index=0):
+        self._check(self.lib.b2p_gen_leaves_device(self.ctx, dev_index, n, key, first_index, d_out, stream))
+
+    def microbench(self, which, iters=2000, dev_index=0):
+        ops, ms = C.c_double(), C.c_double()
+        self._check(self.lib.b2p_microbench(self.ctx, dev_index, which, iters, C.byref(ops), C.byref(ms)))
+        return ops.value, ms.value
+
+
+# ---- converters (no context, no device) -------------------------------------------------------------
+def pack776(states776):
+    lib = load_library()
+    buf = np.ascontiguousarray(states776, dtype=np.uint8).reshape(-1)
+    n = buf.size // STATE776_BYTES
+    out = np.empty((n, 4), dtype=np.uint32)
+    rc = lib.b2p_pack776(_ptr(buf), n, _ptr(out))
+    if rc:
+        raise B2PError("b2p_pack776 failed: %d" % rc)
+    return out
+
+
+def unpack776(states):
+    lib = load_library()
+    a = _as_packed(states)
+    out = np.empty((a.shape[0], STATE776_BYTES), dtype=np.uint8)
+    rc = lib.b2p_unpack776(_ptr(a), a.shape[0], _ptr(out))
+    if rc:
+        raise B2PError("b2p_unpack776 failed: %d" % rc)
+    return out
+
+
+def expand_move(move):
+    lib = load_library()
+    out = np.zeros(MOVE_BYTES, dtype=np.uint8)
+    rc = lib.b2p_expand_move(int(move), _ptr(out))
+    if rc:
+        raise B2PError("b2p_expand_move failed: %d" % rc)
+    return out

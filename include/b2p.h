@@ -1,0 +1,149 @@
+/*
+ * include/b2p.h -- C ABI of the B200-native checkers playout engine (libb2p.so).
+ *
+ * This is the drop-in boundary for ONE hot path of krame505/gpu_ai: batched checkers playouts
+ * from MCTS leaf states behind `PlayoutDriver::runPlayouts(std::vector<State>)`
+ * (reference: src/playout.hpp:27-33).  Every entry point names the reference interface it
+ * replaces.  Plain pointers and sizes only; no C++ or torch types cross this line.  The
+ * reference-side binding (a C++ shim TU that defines the reference's five device symbols on
+ * top of these calls) is shim/playout_shim.cpp; see INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative B2P_E* code; nothing throws or exits
+ *     across the ABI (the reference prints and exit(1)s on CUDA errors,
+ *     src/singlePlayout.cu:91-108).  b2p_last_error() returns the message.
+ *   - a context owns its devices' streams, staging and device buffers (grow-only, reused
+ *     across calls; the reference mallocs and frees on every call, src/singlePlayout.cu:80-116).
+ *   - one context = one caller at a time; different contexts may be used concurrently from
+ *     different host threads (MCTSPlayer worker threads, src/player.cpp:119-150).
+ *   - there is NO CPU execution path: without a usable CUDA device b2p_create fails.
+ *
+ * Packed state (16 bytes): square i = row*4 + col/2 over the 32 dark squares (the numbering of
+ * the reference's genTypeMovesParallel, src/state.cu:185-188).
+ */
+#ifndef B2P_H
+#define B2P_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b2p_ctx b2p_ctx;
+
+/* replaces struct State (776 B AoS, src/state.hpp:119-122) on the device and on the wire */
+typedef struct b2p_state16 {
+  uint32_t p1;    /* PLAYER_1 pieces */
+  uint32_t p2;    /* PLAYER_2 pieces */
+  uint32_t kings; /* kings of both players */
+  uint32_t meta;  /* bit 0: turn (0 = PLAYER_1, 1 = PLAYER_2); bits 8..31: movesSinceLastCapture */
+} b2p_state16;
+
+/* replaces struct Move (38 B, src/state.hpp:253-296) in b2p_genmoves output:
+ * [0:5) from, [5:10) to, [10:13) jumps, [13] promoted, [16+5k : 21+5k) landing square of hop k.
+ * Move::removed[k] is the midpoint of consecutive landings (Move::addJump, src/state.cu:456-462). */
+typedef uint64_t b2p_move_t;
+
+/* winners use the reference's PlayerId values (src/state.hpp:21-26) */
+#define B2P_PLAYER_1 0
+#define B2P_PLAYER_2 1
+#define B2P_PLAYER_NONE (-1)
+#define B2P_UNFINISHED 2 /* only with max_plies >= 0 */
+
+enum { B2P_MODE_RANDOM = 0,     /* HostPlayoutDriver semantics, src/playout.cpp:17-32 */
+       B2P_MODE_HEURISTIC = 1   /* HostHeuristicPlayoutDriver semantics, src/heuristicPlayout.cpp:12-48 */ };
+enum { B2P_SCHED_THREAD = 0,    /* one lane per playout, persistent lanes with warp-aggregated refill
+                                   (replaces singlePlayoutKernel / coarsePlayoutKernel scheduling) */
+       B2P_SCHED_WARP = 1,      /* one warp per playout (replaces playoutKernel / heuristicPlayoutKernel
+                                   scheduling); lowest latency for small batches */
+       B2P_SCHED_AUTO = 2 };
+enum { B2P_ORDER_CANONICAL = 0, /* rank j -> j-th move of State::getMoves() */
+       B2P_ORDER_FAST = 1       /* rank j -> j-th move in direction-major order (same uniform law) */ };
+
+#define B2P_OK 0
+#define B2P_EINVAL (-1)
+#define B2P_ECUDA (-2)
+#define B2P_ENOMEM (-3)
+#define B2P_ENODEV (-4)
+
+typedef struct b2p_devinfo {
+  int device_id;
+  int sm_count;
+  int clock_khz;
+  int cc_major, cc_minor;
+  size_t total_mem;
+  char name[128];
+} b2p_devinfo;
+
+/* ---- lifetime -------------------------------------------------------------------------- */
+/* device_ids == NULL: use devices 0..n_dev-1; n_dev <= 0: all visible devices. */
+int b2p_create(b2p_ctx **out, const int *device_ids, int n_dev, uint64_t seed);
+void b2p_destroy(b2p_ctx *ctx);
+const char *b2p_last_error(const b2p_ctx *ctx); /* ctx may be NULL: error of the last failed b2p_create */
+int b2p_device_count(const b2p_ctx *ctx);
+int b2p_device_info(const b2p_ctx *ctx, int dev_index, b2p_devinfo *out);
+const char *b2p_version(void);
+
+/* ---- the reference-facing call ---------------------------------------------------------------
+ * Replaces Device{Single,Multiple,Coarse,Heuristic}PlayoutDriver::runPlayouts
+ * (src/singlePlayout.cu:71-120, multiplePlayout.cu:53-98, coarsePlayout.cu:91-163,
+ * heuristicPlayout.cu:102-147).  `states` = n reference `State` objects (776 B each) in host
+ * memory; winners_out[i] = PlayerId of a playout from states[i].  Packs on the host, shards
+ * contiguously over the context's devices, plays, gathers.  n == 0 is a no-op.  The RNG stream
+ * is f(context seed, per-context call counter, global leaf index): repeated calls differ (the
+ * reference reuses SEED 12345 every call) but a context replays identically. */
+int b2p_run_states776(b2p_ctx *ctx, const void *states, size_t n, int mode, int sched, int32_t *winners_out);
+
+/* ---- packed host-buffer call ---------------------------------------------------------------
+ * Playout id of (rep, leaf) = pid_base + rep*n + leaf; it is the Philox counter, so results do
+ * not depend on the number of devices.  Outputs (each may be NULL) have n*reps entries in that
+ * order; counters_out = {draws, PLAYER_1 wins, PLAYER_2 wins, plies played} summed over all
+ * devices.  max_plies < 0: play to the end. */
+int b2p_run_packed(b2p_ctx *ctx, const b2p_state16 *states, size_t n, uint32_t reps, uint64_t key, uint64_t pid_base,
+                   int mode, int sched, int order, int max_plies, int8_t *winners_out, uint32_t *plies_out,
+                   b2p_state16 *final_out, uint64_t counters_out[4]);
+
+/* ---- move generation (replaces genMovesKernel / genMovesTest, src/genMovesTest.cu:10-100) ----
+ * moves_out[i*max_moves + k] = k-th move of State::getMoves() for states[i] (k < max_moves);
+ * counts_out[i] = number of legal moves (may exceed max_moves). */
+int b2p_genmoves(b2p_ctx *ctx, const b2p_state16 *states, size_t n, int max_moves, b2p_move_t *moves_out,
+                 uint8_t *counts_out);
+
+/* ---- device-resident calls (single device `dev_index` of the context, asynchronous on
+ * `cuda_stream` (a cudaStream_t, passed through as is: NULL = the CUDA default stream).  All
+ * pointers are device pointers on that device.  counters (4 x u64) are ACCUMULATED with atomics: zero them first. */
+int b2p_run_packed_device(b2p_ctx *ctx, int dev_index, const b2p_state16 *d_states, size_t n, uint32_t reps,
+                          uint64_t key, uint64_t pid_base, int mode, int sched, int order, int max_plies,
+                          int8_t *d_winners, uint32_t *d_plies, b2p_state16 *d_final, uint64_t *d_counters,
+                          void *cuda_stream);
+int b2p_genmoves_device(b2p_ctx *ctx, int dev_index, const b2p_state16 *d_states, size_t n, int max_moves,
+                        b2p_move_t *d_moves, uint8_t *d_counts, void *cuda_stream);
+/* D_ref leaf set: the reference's genRandomStates recipe (src/driver.cpp:76-104) with a
+ * reproducible per-leaf Philox stream; leaf j = first_index + j. */
+int b2p_gen_leaves_device(b2p_ctx *ctx, int dev_index, size_t n, uint64_t key, uint64_t first_index,
+                          b2p_state16 *d_out, void *cuda_stream);
+int b2p_gen_leaves(b2p_ctx *ctx, size_t n, uint64_t key, uint64_t first_index, b2p_state16 *out);
+int b2p_sync(b2p_ctx *ctx);
+
+/* ---- layout converters (host, multi-threaded; no device involved) ------------------------------
+ * struct State <-> b2p_state16.  type/owner are read only where `occupied` is set: State::move
+ * leaves stale fields in vacated squares (src/state.cu:78-84). */
+int b2p_pack776(const void *states, size_t n, b2p_state16 *out);
+int b2p_unpack776(const b2p_state16 *states, size_t n, void *states_out);
+/* b2p_move_t -> struct Move (38 B: from@0 to@2 removed@4 intermediate@20 jumps@36 promoted@37) */
+int b2p_expand_move(b2p_move_t move, void *move38_out);
+
+/* ---- measurement helpers ------------------------------------------------------------------------
+ * Dependency-light integer-pipe microbenchmarks that freeze the INT32 roofline denominator
+ * (SURVEY.md 8d).  which: 0 LOP3, 1 IADD3, 2 SHF, 3 POPC, 4 IMAD, 5 LOP3+IMAD mix, 6 BREV.
+ * Returns thread-level ops per second over the whole chip. */
+int b2p_microbench(b2p_ctx *ctx, int dev_index, int which, int iters, double *thread_ops_per_s, double *ms);
+/* number of kernels this context has launched so far (bench.py reports it as gpu_launches) */
+uint64_t b2p_launch_count(const b2p_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2P_H */

@@ -381,7 +381,7 @@ int or_heuristic_playout(or_state *s, uint64_t key, uint64_t pid, int max_plies,
   or_move mv[OR_MAX_MOVES];
   unsigned score[2];
   material(s, score);
-  uint32_t ply = 0, draws = 0;
+  uint32_t ply = 0;
   int result;
   for (;;) {
     int n = or_gen_moves(s, mv);
@@ -395,7 +395,7 @@ int or_heuristic_playout(or_state *s, uint64_t key, uint64_t pid, int max_plies,
       int d_me = mv[i].crowned ? 3 : 0, d_you = 0;
       for (int k = 0; k < mv[i].hops; k++) d_you -= s->at[mv[i].cap_r[k]][mv[i].cap_c[k]].king ? 4 : 1;
       unsigned a = score[me] + (unsigned)d_me, b = score[you] + (unsigned)d_you;
-      float w = (float)a / (float)b + ch_gauss_sigma(ch_draw(key, pid, CH_DOMAIN_NOISE, draws++));
+      float w = (float)a / (float)b + ch_gauss_sigma(ch_noise_draw(key, pid, ply, (uint32_t)i));
       if (w > best_w) { best_w = w; best = i; best_d_me = d_me; best_d_you = d_you; }
     }
     or_apply(s, &mv[best]);

@@ -136,7 +136,7 @@ int heuristic_playout(State &s, uint64_t key, uint64_t pid, int max_plies, uint3
   Move mv[MAX_MOVES];
   unsigned stateScore[NUM_PLAYERS];
   scoreState(s, stateScore);
-  uint32_t ply = 0, draws = 0;
+  uint32_t ply = 0;
   int res;
   for (;;) {
     int n = s.genMoves(mv);
@@ -151,7 +151,7 @@ int heuristic_playout(State &s, uint64_t key, uint64_t pid, int max_plies, uint3
       scoreMove(s, mv[i], ms);
       d[2 * i] = ms[0];
       d[2 * i + 1] = ms[1];
-      float w = getWeight(s, stateScore, ms) + ch_gauss_sigma(ch_draw(key, pid, CH_DOMAIN_NOISE, draws++));
+      float w = getWeight(s, stateScore, ms) + ch_gauss_sigma(ch_noise_draw(key, pid, ply, (uint32_t)i));
       if (w > bestW) { bestW = w; best = i; }
     }
     s.move(mv[best]);

@@ -1,0 +1,177 @@
+"""GPU (B200): the CUDA path, called through the C ABI, against the oracle and the golden vectors.
+
+Three parity gates of BASELINE.json's north_star:
+  1. move generation bit-exact against the reference's State::getMoves (>= 10^6 positions);
+  2. playouts driven by an injected deterministic move-choice sequence give bit-exact winners
+     (and ply counts, and final states);
+  3. random and heuristic win rates match the reference's host drivers within a binomial CI.
+Plus size-independent properties at the full benchmark size (2^20 leaves).
+"""
+import numpy as np
+import pytest
+
+from conftest import fast_synthetic, unflatten
+from oracle.pyoracle import MODE_HEURISTIC, MODE_RANDOM, ORDER_CANONICAL, ORDER_FAST, START_PACKED
+
+pytestmark = pytest.mark.gpu
+
+
+# ---- gate 1: move generation ----------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["leaves", "synth", "kat"])
+def test_genmoves_equals_golden(engine, golden, name):
+    st, cnt = golden[name + "_states"], golden[name + "_counts"]
+    mv, c = engine.genmoves(st, 64)
+    assert np.array_equal(c, cnt)
+    assert np.array_equal(mv, unflatten(golden[name + "_moves_flat"], cnt))
+
+
+def test_genmoves_million_positions_bit_exact(engine, port):
+    leaves = engine.gen_leaves(1 << 20, key=31337)
+    assert np.array_equal(leaves[:50000], port.gen_leaves(50000, key=31337))
+    st = np.concatenate([leaves, fast_synthetic(1 << 19, 3)])
+    a, ca = engine.genmoves(st, 48)
+    b, cb = port.genmoves(st, 48)
+    assert cb.max() <= 48
+    assert np.array_equal(ca, cb)
+    assert np.array_equal(a, b)
+
+
+def test_genmoves_truncation_and_edge_sizes(engine, golden):
+    st, cnt = golden["leaves_states"][:100], golden["leaves_counts"][:100]
+    mv, c = engine.genmoves(st, 2)           # max_moves smaller than the list: counts stay true
+    assert np.array_equal(c, cnt)
+    full = unflatten(golden["leaves_moves_flat"], golden["leaves_counts"])[:100]
+    assert np.array_equal(mv, full[:, :2])
+    mv, c = engine.genmoves(np.zeros((0, 4), np.uint32), 8)   # empty input
+    assert mv.shape == (0, 8) and c.shape == (0,)
+    mv, c = engine.genmoves(st[:1], 64)      # single state
+    assert c[0] == cnt[0]
+
+
+# ---- gate 2: deterministic replay -----------------------------------------------------------------
+@pytest.mark.parametrize("name", ["leaves", "synth"])
+@pytest.mark.parametrize("tag,mode,order", [("rc", MODE_RANDOM, ORDER_CANONICAL), ("rf", MODE_RANDOM, ORDER_FAST),
+                                            ("h", MODE_HEURISTIC, ORDER_CANONICAL)])
+def test_playouts_equal_golden(engine, golden, name, tag, mode, order):
+    st = golden[name + "_states"]
+    w, p, f, c = engine.run_packed(st, reps=2, key=12345, pid_base=1000, mode=mode, order=order,
+                                   want_plies=True, want_final=True)
+    assert np.array_equal(w, golden["%s_%s_winners" % (name, tag)])
+    assert np.array_equal(p, golden["%s_%s_plies" % (name, tag)])
+    assert np.array_equal(f, golden["%s_%s_final" % (name, tag)])
+    assert np.array_equal(c, golden["%s_%s_counters" % (name, tag)])
+
+
+@pytest.mark.parametrize("mode,order", [(MODE_RANDOM, ORDER_CANONICAL), (MODE_RANDOM, ORDER_FAST), (MODE_HEURISTIC, ORDER_CANONICAL)])
+def test_playouts_equal_oracle_large(engine, port, mode, order):
+    st = np.concatenate([engine.gen_leaves(150000, key=77), fast_synthetic(50000, 19)])
+    w, p, f, c = engine.run_packed(st, key=99, pid_base=12, mode=mode, order=order, want_plies=True, want_final=True)
+    ow, op, of, oc = port.playouts(st, key=99, pid_base=12, mode=mode, order=order, want_final=True)
+    assert np.array_equal(w, ow) and np.array_equal(p, op) and np.array_equal(f, of) and np.array_equal(c, oc)
+
+
+def test_fast_kernel_without_optional_outputs_matches(engine, port):
+    """the lean kernel variant (winners + counters only) is the one the benchmark times"""
+    st = engine.gen_leaves(100000, key=5)
+    w, _, _, c = engine.run_packed(st, reps=3, key=31, mode=MODE_RANDOM, order=ORDER_FAST)
+    ow, _, _, oc = port.playouts(st, reps=3, key=31, mode=MODE_RANDOM, order=ORDER_FAST)
+    assert np.array_equal(w, ow) and np.array_equal(c, oc)
+
+
+@pytest.mark.parametrize("name", ["leaves", "synth"])
+def test_truncated_playouts_equal_golden(engine, golden, name):
+    w, p, f, c = engine.run_packed(golden[name + "_states"], key=12345, max_plies=5, want_plies=True, want_final=True)
+    assert np.array_equal(w, golden[name + "_cut5_winners"])
+    assert np.array_equal(f, golden[name + "_cut5_final"])
+
+
+def test_leafgen_equals_golden(engine, golden):
+    assert np.array_equal(engine.gen_leaves(4096, key=2016), golden["leaves_states"])
+    # leaf j does not depend on the batch it was generated in
+    assert np.array_equal(engine.gen_leaves(1000, key=2016, first_index=3000), golden["leaves_states"][3000:4000])
+
+
+def test_terminal_and_degenerate_inputs(engine, golden):
+    names = list(golden["kat_names"])
+    w, _, _, _ = engine.run_packed(golden["kat_states"], key=12345)
+    assert np.array_equal(w, golden["kat_rc_winners"])
+    assert w[names.index("no_pieces_to_move")] == 1 and w[names.index("draw_counter")] == -1
+    w, _, _, c = engine.run_packed(np.zeros((0, 4), np.uint32))          # empty batch
+    assert w.shape == (0,) and c.sum() == 0
+    w, _, _, _ = engine.run_packed(START_PACKED.reshape(1, 4), reps=1)   # batch of one
+    assert w[0] in (-1, 0, 1)
+
+
+def test_results_do_not_depend_on_batch_split(engine):
+    """RNG is keyed by the global playout id: playing a batch in two halves gives the same winners."""
+    st = engine.gen_leaves(20001, key=8)
+    w, _, _, _ = engine.run_packed(st, key=5, pid_base=0, order=ORDER_FAST)
+    a, _, _, _ = engine.run_packed(st[:7777], key=5, pid_base=0, order=ORDER_FAST)
+    b, _, _, _ = engine.run_packed(st[7777:], key=5, pid_base=7777, order=ORDER_FAST)
+    assert np.array_equal(w, np.concatenate([a, b]))
+
+
+# ---- the reference-facing 776-byte entry point -----------------------------------------------------------
+def test_run_states776_drop_in(engine, port, golden):
+    import gpu_ai_b200 as b
+    st = golden["leaves_states"]
+    s776 = port.unpack776(st)
+    for name in ("device_single", "device_multiple", "device_coarse", "device_heuristic"):
+        drv = b.getPlayoutDriver(name)
+        assert drv.getName() == name
+        res = drv.runPlayouts(s776)
+        assert res.dtype == np.int32 and res.shape == (len(st),)
+        assert set(np.unique(res)) <= {-1, 0, 1}
+        # states that are already over must come back with their winner (src/mcts.cpp:65-68)
+        term = golden["leaves_counts"] == 0
+        assert np.array_equal(res[term], golden["leaves_rc_winners"][:len(st)][term])
+        assert drv.runPlayouts(np.zeros((0, 776), np.uint8)).shape == (0,)
+
+
+# ---- gate 3: win-rate statistics vs the reference's own host drivers ------------------------------------
+def _z(count_a, n_a, count_b, n_b):
+    pa, pb = count_a / n_a, count_b / n_b
+    p = (count_a + count_b) / (n_a + n_b)
+    se = np.sqrt(p * (1 - p) * (1 / n_a + 1 / n_b))
+    return (pa - pb) / se
+
+
+@pytest.mark.parametrize("tag,mode", [("host", MODE_RANDOM), ("host_heuristic", MODE_HEURISTIC)])
+def test_winrates_match_reference_host_driver(engine, golden, tag, mode):
+    """Two-proportion z-test on draws / P1 wins / P2 wins: GPU (Philox) vs the reference's
+    HostPlayoutDriver / HostHeuristicPlayoutDriver (glibc rand / std::normal_distribution) on the same
+    65536 D_ref leaves.  Tolerance: |z| < 4 on each outcome (two-sided p ~ 6e-5 per test)."""
+    ref_tally = golden["ref_%s_tally_65536" % tag]
+    st = engine.gen_leaves(65536, key=2016)
+    reps = 16
+    _, _, _, c = engine.run_packed(st, reps=reps, key=424242, mode=mode, order=ORDER_CANONICAL if mode else ORDER_FAST,
+                                   want_winners=False)
+    n_gpu, n_ref = 65536 * reps, 65536
+    assert int(c[0] + c[1] + c[2]) == n_gpu
+    for k in range(3):
+        z = _z(int(c[k]), n_gpu, int(ref_tally[k]), n_ref)
+        assert abs(z) < 4.0, "outcome %d: gpu %.4f vs reference %.4f (z = %.2f)" % (k, c[k] / n_gpu, ref_tally[k] / n_ref, z)
+
+
+# ---- size-independent properties at the full benchmark size ------------------------------------------------
+def test_full_size_properties(engine):
+    n = 1 << 20
+    st = engine.gen_leaves(n, key=2016)
+    w, p, f, c = engine.run_packed(st, key=1, order=ORDER_FAST, want_plies=True, want_final=True)
+    # counters are a checksum of the per-playout outputs
+    assert int(c[0]) == int((w == -1).sum()) and int(c[1]) == int((w == 0).sum()) and int(c[2]) == int((w == 1).sum())
+    assert int(c[3]) == int(p.sum(dtype=np.uint64))
+    # every playout ends, and ends in a terminal state: a second pass from the final states plays 0 plies
+    assert set(np.unique(w)) <= {-1, 0, 1}
+    w2, p2, f2, _ = engine.run_packed(f, key=2, order=ORDER_FAST, want_plies=True, want_final=True)
+    assert p2.max() == 0 and np.array_equal(w2, w) and np.array_equal(f2, f)
+    # a draw is declared exactly when the counter reached 50
+    assert np.array_equal((f[:, 3] >> 8) >= 50, w == -1)
+    # material never appears from nowhere
+    pop = lambda a: np.unpackbits(a.view(np.uint8)).reshape(len(a), -1).sum(axis=1)  # noqa: E731
+    assert (pop(f[:, 0].copy()) <= pop(st[:, 0].copy())).all() and (pop(f[:, 1].copy()) <= pop(st[:, 1].copy())).all()
+    # determinism: same key -> same winners; different key -> different stream
+    w3, _, _, _ = engine.run_packed(st, key=1, order=ORDER_FAST)
+    assert np.array_equal(w3, w)
+    w4, _, _, _ = engine.run_packed(st, key=2, order=ORDER_FAST)
+    assert 0.5 < (w4 == w).mean() < 0.95

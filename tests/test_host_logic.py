@@ -1,0 +1,59 @@
+"""CPU: the product's bit logic (bitboard.cuh / philox.cuh / playout_core.cuh compiled with g++ by
+tests/host_build) against the oracle.  Same code the kernels inline; no GPU needed."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import fast_synthetic, unflatten
+from oracle.pyoracle import MODE_HEURISTIC, MODE_RANDOM, ORDER_CANONICAL, ORDER_FAST
+
+
+def test_hostbuild_philox(hostbuild):
+    o = (C.c_uint32 * 4)()
+    hostbuild.lib.hb_philox((C.c_uint32 * 4)(0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344),
+                            (C.c_uint32 * 2)(0xa4093822, 0x299f31d0), o)
+    assert list(o) == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+@pytest.mark.parametrize("name", ["leaves", "synth", "kat"])
+def test_bitboard_movelists_equal_golden(hostbuild, golden, name):
+    st, cnt = golden[name + "_states"], golden[name + "_counts"]
+    mv, c = hostbuild.genmoves(st, 64)
+    assert np.array_equal(c, cnt)
+    assert np.array_equal(mv, unflatten(golden[name + "_moves_flat"], cnt))
+
+
+def test_bitboard_movelists_million_positions(hostbuild, port):
+    """bit-exact genMoves on >= 10^6 positions: reachable leaves + king-rich synthetic boards"""
+    st = np.concatenate([port.gen_leaves(600000, key=31337), fast_synthetic(600000, 3)])
+    a, ca = hostbuild.genmoves(st, 64)
+    b, cb = port.genmoves(st, 64)
+    assert ca.max() <= 64
+    assert np.array_equal(ca, cb)
+    assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("name", ["leaves", "synth"])
+@pytest.mark.parametrize("tag,mode,order", [("rc", MODE_RANDOM, ORDER_CANONICAL), ("rf", MODE_RANDOM, ORDER_FAST),
+                                            ("h", MODE_HEURISTIC, ORDER_CANONICAL)])
+def test_ply_step_equals_golden(hostbuild, golden, name, tag, mode, order):
+    st = golden[name + "_states"]
+    w, p, f, c = hostbuild.playouts(st, reps=2, key=12345, pid_base=1000, mode=mode, order=order, want_final=True)
+    assert np.array_equal(w, golden["%s_%s_winners" % (name, tag)])
+    assert np.array_equal(p, golden["%s_%s_plies" % (name, tag)])
+    assert np.array_equal(f, golden["%s_%s_final" % (name, tag)])
+    assert np.array_equal(c, golden["%s_%s_counters" % (name, tag)])
+
+
+@pytest.mark.parametrize("mode,order", [(MODE_RANDOM, ORDER_CANONICAL), (MODE_RANDOM, ORDER_FAST), (MODE_HEURISTIC, ORDER_CANONICAL)])
+def test_ply_step_equals_port_large(hostbuild, port, mode, order):
+    st = np.concatenate([port.gen_leaves(40000, key=77), fast_synthetic(40000, 19)])
+    a = hostbuild.playouts(st, key=99, pid_base=12, mode=mode, order=order, want_final=True)
+    b = port.playouts(st, key=99, pid_base=12, mode=mode, order=order, want_final=True)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+
+
+def test_leafgen_equals_golden(hostbuild, golden):
+    assert np.array_equal(hostbuild.gen_leaves(4096, key=2016), golden["leaves_states"])
