@@ -41,59 +41,154 @@ B2P_HD void store_game(const Game &g, uint32_t out[4]) {
   out[3] = g.turn | ((g.msc > 0xFFFFFFu ? 0xFFFFFFu : g.msc) << 8);
 }
 
+// ---- multi-hop captures ----------------------------------------------------------------------
+// Exact number of complete capture sequences of a MAN standing on (or landing on) square s, for
+// all 32 squares at once.  Men only hop upward (UL = +7 through E1, UR = +9 through E0), the
+// board is static during a sequence, so the sequences below s form a DAG of height <= 3 and
+//   count(s) = 1                                   if no hop leaves s
+//            = [E1(s)] count(s+7) + [E0(s)] count(s+9)   otherwise
+// Three rounds of a bit-sliced adder (values <= 8: planes t[0..3]) replace the reference's
+// recursion (genLocCaptureReg, src/state.cu:283-340) -- ~35 LOP3/SHF for the whole board.
+struct ManCounts {
+  uint32_t t[4];
+};
+
+B2P_HD ManCounts man_leaf_counts(uint32_t E0, uint32_t E1) {
+  const uint32_t none = ~(E0 | E1);
+  // height <= 1: 1 or 2
+  const uint32_t b1 = E0 & E1, b0 = ~b1;
+  // height <= 2
+  uint32_t a0 = E1 & (b0 >> 7), a1 = E1 & (b1 >> 7);
+  uint32_t d0 = E0 & (b0 >> 9), d1 = E0 & (b1 >> 9);
+  uint32_t cy = a0 & d0;
+  const uint32_t s0 = (a0 ^ d0) | none;
+  const uint32_t s1 = a1 ^ d1 ^ cy;
+  const uint32_t s2 = (a1 & d1) | (cy & (a1 ^ d1));
+  // height <= 3
+  a0 = E1 & (s0 >> 7); a1 = E1 & (s1 >> 7);
+  const uint32_t a2 = E1 & (s2 >> 7);
+  d0 = E0 & (s0 >> 9); d1 = E0 & (s1 >> 9);
+  const uint32_t d2 = E0 & (s2 >> 9);
+  ManCounts m;
+  cy = a0 & d0;
+  m.t[0] = (a0 ^ d0) | none;
+  m.t[1] = a1 ^ d1 ^ cy;
+  cy = (a1 & d1) | (cy & (a1 ^ d1));
+  m.t[2] = a2 ^ d2 ^ cy;
+  m.t[3] = (a2 & d2) | (cy & (a2 ^ d2));
+  return m;
+}
+
+B2P_HD int man_count_at(const ManCounts &m, int s) {
+  return (int)(((m.t[0] >> s) & 1u) | (((m.t[1] >> s) & 1u) << 1) | (((m.t[2] >> s) & 1u) << 2) | (((m.t[3] >> s) & 1u) << 3));
+}
+
+// The rare path: some capture can be extended by a second hop.  Picks sequence number
+// mulhi32(r, n) (reversed for `reverse`) of the normalised canonical list.  Men are counted and
+// selected through the bit-sliced DAG counts; only a KING that can hop twice falls back to the
+// register DFS (visited-square rule, src/state.cu:134-139).
+B2P_HD void pick_multi_hop_capture(const Pos &p, const JumpMasks &jm, const uint32_t cap[4], uint32_t r, bool reverse,
+                                   uint32_t &from, uint32_t &to, uint32_t &captured) {
+  const uint32_t K = p.kings;
+  const uint32_t anyJ = jm.j[0] | jm.j[1] | jm.j[2] | jm.j[3];
+  const uint32_t land_king = jumpUR(cap[0] & K) | jumpUL(cap[1] & K) | jumpDR(cap[2]) | jumpDL(cap[3]);
+  if (land_king & anyJ) {
+    const int n = for_each_capture(p, jm, [](const CaptureMove &) { return false; });
+    int k = (int)mulhi(r, (uint32_t)n);
+    if (reverse) k = n - 1 - k;
+    from = to = captured = 0;
+    for_each_capture(p, jm, [&](const CaptureMove &cm) {
+      if (k-- != 0) return false;
+      from = 1u << cm.from; to = 1u << cm.to; captured = cm.captured;
+      return true;
+    });
+    return;
+  }
+  const uint32_t E0 = jm.j[0], E1 = jm.j[1];
+  const ManCounts mc = man_leaf_counts(E0, E1);
+  const uint32_t M = (cap[0] | cap[1]) & ~K;
+  const int n = popc(mc.t[0] & M) + 2 * popc(mc.t[1] & M) + 4 * popc(mc.t[2] & M) + 8 * popc(mc.t[3] & M) +
+                popc(cap[0] & K) + popc(cap[1] & K) + popc(cap[2]) + popc(cap[3]);
+  int k = (int)mulhi(r, (uint32_t)n);
+  if (reverse) k = n - 1 - k;
+  uint32_t origins = cap[0] | cap[1] | cap[2] | cap[3];
+  int o;
+  bool king;
+  for (;;) {
+    o = lowbit(origins);
+    king = (K >> o) & 1u;
+    const int w = king ? (int)(((cap[0] >> o) & 1u) + ((cap[1] >> o) & 1u) + ((cap[2] >> o) & 1u) + ((cap[3] >> o) & 1u))
+                       : man_count_at(mc, o);
+    if (k < w) break;
+    k -= w;
+    origins &= origins - 1;
+  }
+  from = 1u << o;
+  if (king) {
+    uint32_t nib = ((cap[0] >> o) & 1u) | (((cap[1] >> o) & 1u) << 1) | (((cap[2] >> o) & 1u) << 2) | (((cap[3] >> o) & 1u) << 3);
+    if (k >= 1) nib &= nib - 1;
+    if (k >= 2) nib &= nib - 1;
+    if (k >= 3) nib &= nib - 1;
+    const int d = lowbit(nib);
+    to = 1u << jump_target(o, d);
+    captured = 1u << step_target(o, d);
+  } else {
+    int cur = o;
+    captured = 0;
+    while (((E0 | E1) >> cur) & 1u) {
+      const int left = ((E1 >> cur) & 1u) ? man_count_at(mc, cur + 7) : 0;  // UL subtree first (left before right)
+      if (k < left) {
+        captured |= 1u << step_target(cur, 1);
+        cur += 7;
+      } else {
+        k -= left;
+        captured |= 1u << step_target(cur, 0);
+        cur += 9;
+      }
+    }
+    to = 1u << cur;
+  }
+}
+
 // One ply with a uniformly random legal move chosen by the 32-bit draw r:
 // rank j = mulhi32(r, n) in the list order ORDER (bitboard.cuh).  Returns kRunning, or the
 // winner when the game is over BEFORE a move is made: -1 if msc >= 50 (the draw test wins
 // over "no moves", src/state.cpp:20-23), else the player who is not to move.
+//
+// Direct moves and single-hop captures share one branch-free path (four origin masks ->
+// popc -> rank -> k-th bit): the warp stays converged whether or not a lane must capture.
 template <int ORDER>
 B2P_HD int random_ply(Game &g, uint32_t r) {
   if (g.msc >= kDrawPlies) return -1;
   const Pos p = g.pos;
-  const JumpMasks jm = jump_masks(p);
-  uint32_t a[4];
-  capture_origins(p, jm, a);
+  const uint32_t empty = ~(p.own | p.opp);
+  const uint32_t ownK = p.own & p.kings;
+  // squares from which one step in direction d reaches an empty square
+  const uint32_t e0 = stepDL(empty), e1 = stepDR(empty), e2 = stepUL(empty), e3 = stepUR(empty);
+  JumpMasks jm;
+  jm.j[0] = stepDL(p.opp & e0);
+  jm.j[1] = stepDR(p.opp & e1);
+  jm.j[2] = stepUL(p.opp & e2);
+  jm.j[3] = stepUR(p.opp & e3);
+  uint32_t cap[4] = {p.own & jm.j[0], p.own & jm.j[1], ownK & jm.j[2], ownK & jm.j[3]};
+  const bool capture = (cap[0] | cap[1] | cap[2] | cap[3]) != 0;
   uint32_t from, to, captured;
-  if ((a[0] | a[1] | a[2] | a[3]) != 0) {
-    if (!any_second_hop(p, jm, a)) {
-      // every capture is a single hop: one list entry per (origin, direction)
-      if (ORDER == kOrderCanonical) {
-        // reference slot order at one origin: man UL,UR (left first); king UR,UL,DR,DL
-        const uint32_t men = ~p.kings;
-        const uint32_t s0 = (a[1] & men) | (a[0] & p.kings);
-        const uint32_t s1 = (a[0] & men) | (a[1] & p.kings);
-        a[0] = s0; a[1] = s1;
-      }
-      const int n0 = popc(a[0]), n1 = popc(a[1]), n2 = popc(a[2]);
-      const int n = n0 + n1 + n2 + popc(a[3]);
-      int k = (int)mulhi(r, (uint32_t)n);
-      int sel;
-      if (ORDER == kOrderCanonical) {
-        if (g.turn) k = n - 1 - k;
-        sel = select_origin_major(a, k);
-      } else {
-        sel = select_dir_major(a, n0, n1, n2, k);
-      }
-      const int o = sel & 31;
-      int d = sel >> 5;
-      if (ORDER == kOrderCanonical && !((p.kings >> o) & 1u)) d ^= 1;
-      from = 1u << o;
-      to = 1u << jump_target(o, d);
-      captured = 1u << step_target(o, d);
-    } else {
-      // multi-hop sequences exist: count, then walk to the chosen one
-      const int n = for_each_capture(p, jm, [](const CaptureMove &) { return false; });
-      int k = (int)mulhi(r, (uint32_t)n);
-      if (ORDER == kOrderCanonical && g.turn) k = n - 1 - k;
-      from = to = captured = 0;
-      for_each_capture(p, jm, [&](const CaptureMove &cm) {
-        if (k-- != 0) return false;
-        from = 1u << cm.from; to = 1u << cm.to; captured = cm.captured;
-        return true;
-      });
-    }
-    g.msc = 0;
+  if (capture && any_second_hop(p, jm, cap)) {
+    pick_multi_hop_capture(p, jm, cap, r, ORDER == kOrderCanonical && g.turn != 0, from, to, captured);
   } else {
-    step_origins(p, a);
+    uint32_t a[4];
+    if (ORDER == kOrderCanonical) {
+      // reference slot order at one origin: capturing man UL,UR (left first); everything else UR,UL,DR,DL
+      const uint32_t men = ~p.kings;
+      const uint32_t c0 = (cap[1] & men) | (cap[0] & p.kings), c1 = (cap[0] & men) | (cap[1] & p.kings);
+      a[0] = capture ? c0 : (p.own & e0);
+      a[1] = capture ? c1 : (p.own & e1);
+    } else {
+      a[0] = capture ? cap[0] : (p.own & e0);
+      a[1] = capture ? cap[1] : (p.own & e1);
+    }
+    a[2] = capture ? cap[2] : (ownK & e2);
+    a[3] = capture ? cap[3] : (ownK & e3);
     const int n0 = popc(a[0]), n1 = popc(a[1]), n2 = popc(a[2]);
     const int n = n0 + n1 + n2 + popc(a[3]);
     if (n == 0) return (int)(g.turn ^ 1u);
@@ -105,12 +200,15 @@ B2P_HD int random_ply(Game &g, uint32_t r) {
     } else {
       sel = select_dir_major(a, n0, n1, n2, k);
     }
-    const int o = sel & 31, d = sel >> 5;
+    const int o = sel & 31;
+    int d = sel >> 5;
+    if (ORDER == kOrderCanonical && capture && !((p.kings >> o) & 1u)) d ^= 1;
+    const int mid = step_target(o, d);
     from = 1u << o;
-    to = 1u << step_target(o, d);
-    captured = 0;
-    g.msc++;
+    to = 1u << (capture ? jump_target(o, d) : mid);
+    captured = capture ? (1u << mid) : 0u;
   }
+  g.msc = capture ? 0u : g.msc + 1u;
   Pos q = p;
   apply_move(q, from, to, captured);
   g.pos = flip(q);
