@@ -173,6 +173,7 @@ def main():
     import torch
     import torch.distributed as dist
     import gpu_ai_b200 as b
+    from gpu_ai_b200 import sharding
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -193,7 +194,8 @@ def main():
 
     # ---- synthetic input, generated on the device by the leaf kernel (bit-exact vs oracle: tests) ----
     d_states = torch.empty((n, 4), dtype=torch.int32, device=dev)
-    eng.gen_leaves_device(n, d_states.data_ptr(), key=LEAF_KEY, first_index=rank * n, stream=stream)
+    leaf_lo, _ = sharding.weak_shard(n, rank)
+    eng.gen_leaves_device(n, d_states.data_ptr(), key=LEAF_KEY, first_index=leaf_lo, stream=stream)
     d_winners = torch.empty(n * reps, dtype=torch.int8, device=dev)
     d_counters = torch.zeros(4, dtype=torch.int64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
@@ -203,8 +205,7 @@ def main():
         d_counters.zero_()
         eng.run_packed_device(d_states.data_ptr(), n, reps=reps, key=PLAY_KEY + i, pid_base=rank * n * reps, mode=mode,
                               order=order, d_winners=d_winners.data_ptr(), d_counters=d_counters.data_ptr(), stream=stream)
-        if world > 1:
-            dist.all_reduce(d_counters)   # the single small NCCL all-reduce per iteration (32 bytes)
+        sharding.allreduce_counters(d_counters)   # the single small NCCL all-reduce per iteration (32 bytes)
 
     for i in range(args.warmup):
         step(i)
@@ -242,10 +243,7 @@ def main():
     counters = d_counters.cpu().numpy().astype(np.int64)   # last step, summed over ranks if world > 1
     plies_per_playout = float(counters[3]) / float(max(1, counters[:3].sum()))
 
-    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(t.item())
+    elapsed_ms = sharding.max_over_ranks(elapsed_ms, dev)
     playouts_per_step = n * reps * world
     value = playouts_per_step * args.steps / (elapsed_ms * 1e-3)
 
@@ -306,10 +304,7 @@ def main():
         for _ in range(k):
             eng.run_states776(s776, mode=mode_i, out=res)
         dt = time.perf_counter() - t_start
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
+        dt = sharding.max_over_ranks(dt, dev)
         out["e2e"] = {"value": n * world * k / dt, "unit": "playouts/s", "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": n,
                       "ms_per_call": 1e3 * dt / k, "host_input_bytes_per_step": 776 * n,
                       "api": "b2p_run_states776(host State[776 B] x n) -> int32 PlayerId[n]; pack + H2D + kernel + D2H timed"}
