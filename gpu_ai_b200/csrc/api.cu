@@ -100,6 +100,16 @@ unsigned int *next_slot(Device &d) {
   return p;
 }
 
+// B2P_SCHED_AUTO: warp-per-playout only pays below the batch size at which thread-per-playout
+// fills the machine's latency budget (measured on B200, profiles/: see DESIGN.md 4.5)
+// (profiles/r01d_sched_compare.jsonl: random playouts cross over between 4096 and 8192 playouts per
+// launch, heuristic playouts between 8192 and 32768)
+constexpr size_t kAutoWarpMaxRandom = 4096, kAutoWarpMaxHeuristic = 16384;
+bool use_warp_kernel(int sched, size_t total, KernelMode km) {
+  return sched == B2P_SCHED_WARP ||
+         (sched == B2P_SCHED_AUTO && total <= (km == kHeuristic ? kAutoWarpMaxHeuristic : kAutoWarpMaxRandom));
+}
+
 bool mode_to_kernel(int mode, int order, KernelMode *out) {
   if (mode == B2P_MODE_RANDOM && order == B2P_ORDER_CANONICAL) { *out = kRandomCanonical; return true; }
   if (mode == B2P_MODE_RANDOM && order == B2P_ORDER_FAST) { *out = kRandomFast; return true; }
@@ -340,7 +350,7 @@ int b2p_run_packed_device(b2p_ctx *ctx, int dev_index, const b2p_state16 *d_stat
   prm.counters = reinterpret_cast<unsigned long long *>(d_counters);
   prm.next = next_slot(d);
   cudaError_t e;
-  if (sched == B2P_SCHED_WARP) e = launch_playout_warp(prm, km, d.sm_count, st, nullptr);
+  if (use_warp_kernel(sched, (size_t)n * reps, km)) e = launch_playout_warp(prm, km, d.sm_count, st, nullptr);
   else e = launch_playout_lanes(prm, km, d.sm_count, st, nullptr);
   if (e != cudaSuccess) return fail(ctx, B2P_ECUDA, std::string("playout launch: ") + cudaGetErrorString(e));
   ctx->launches++;
@@ -428,8 +438,8 @@ int b2p_run_packed(b2p_ctx *ctx, const b2p_state16 *states, size_t n, uint32_t r
     prm.final_states = final_out ? (uint4 *)d.d_final.ptr : nullptr;
     prm.counters = (unsigned long long *)d.d_misc.ptr;
     prm.next = next_slot(d);
-    cudaError_t e = sched == B2P_SCHED_WARP ? launch_playout_warp(prm, km, d.sm_count, d.stream, nullptr)
-                                            : launch_playout_lanes(prm, km, d.sm_count, d.stream, nullptr);
+    cudaError_t e = use_warp_kernel(sched, prm.total, km) ? launch_playout_warp(prm, km, d.sm_count, d.stream, nullptr)
+                                                      : launch_playout_lanes(prm, km, d.sm_count, d.stream, nullptr);
     if (e != cudaSuccess) return fail(ctx, B2P_ECUDA, std::string("playout launch: ") + cudaGetErrorString(e));
     ctx->launches++;
     // gather: device layout [rep][local leaf] -> host layout [rep][global leaf]
@@ -490,8 +500,8 @@ int b2p_run_states776(b2p_ctx *ctx, const void *states, size_t n, int mode, int 
     prm.max_plies = -1;
     prm.winners = (int8_t *)d.d_winners.ptr;
     prm.next = next_slot(d);
-    cudaError_t e = sched == B2P_SCHED_WARP ? launch_playout_warp(prm, km, d.sm_count, d.stream, nullptr)
-                                            : launch_playout_lanes(prm, km, d.sm_count, d.stream, nullptr);
+    cudaError_t e = use_warp_kernel(sched, prm.total, km) ? launch_playout_warp(prm, km, d.sm_count, d.stream, nullptr)
+                                                      : launch_playout_lanes(prm, km, d.sm_count, d.stream, nullptr);
     if (e != cudaSuccess) return fail(ctx, B2P_ECUDA, std::string("playout launch: ") + cudaGetErrorString(e));
     ctx->launches++;
     B2P_CUDA(ctx, cudaMemcpyAsync(d.h_winners.ptr, d.d_winners.ptr, nl, cudaMemcpyDeviceToHost, d.stream));

@@ -239,70 +239,80 @@ struct CaptureMove {
   uint64_t path;      // landing square of hop k in bits [5k, 5k+5)
 };
 
-// Calls visit(const CaptureMove&) for sequence number 0,1,2,...; visit returns true to stop.
-// Returns the number of sequences visited.
+// Sequences that start on square `o` (which must hold a piece of the mover with a first hop).
+// Calls visit(const CaptureMove&) for each complete sequence in reference order; visit returns
+// true to stop (then `stopped` is set).  Returns the number of sequences visited.
+template <class Visit>
+B2P_HD int for_each_capture_from(const Pos &p, const JumpMasks &m, int o, Visit &&visit, bool &stopped) {
+  int count = 0;
+  const bool king = (p.kings >> o) & 1u;
+  int cur = o, depth = 0;
+  uint32_t next = 0;       // next slot to try at each depth
+  uint32_t visited = 0;    // landing squares of the current sequence
+  uint32_t captured = 0;
+  uint64_t path = 0;
+  for (;;) {
+    // slots that can be hopped from `cur` (slot order = reference order for this piece type)
+    uint32_t v;
+    if (king) {
+      v = 0;
+      for (int d = 0; d < 4; d++) {
+        const int land = jump_target(cur, d);
+        const uint32_t ok = (m.j[d] >> cur) & 1u;
+        // land may be out of range when ok == 0; guard the shift
+        const uint32_t seen = ok ? ((visited >> (land & 31)) & 1u) : 0u;
+        v |= (ok & ~seen) << d;
+      }
+    } else {
+      v = ((m.j[1] >> cur) & 1u) | (((m.j[0] >> cur) & 1u) << 1);
+    }
+    const int ns = (int)((next >> (3 * depth)) & 7u);
+    const uint32_t todo = v & (0xFu << ns);
+    if (todo == 0) {
+      if (v == 0 && depth > 0) {
+        CaptureMove cm;
+        cm.from = o; cm.to = cur; cm.hops = depth; cm.captured = captured; cm.path = path;
+        count++;
+        if (visit(cm)) { stopped = true; return count; }
+      }
+      if (depth == 0) break;
+      // pop: undo the hop that led to `cur`
+      depth--;
+      const int slot = (int)((next >> (3 * depth)) & 7u) - 1;
+      const int d = king ? slot : (slot ^ 1);
+      const int parent = cur - (jump_target(cur, d) - cur);
+      visited &= ~(1u << cur);
+      captured &= ~(1u << step_target(parent, d));
+      path &= ~((uint64_t)31 << (5 * depth));
+      cur = parent;
+    } else {
+      const int slot = lowbit(todo);
+      const int d = king ? slot : (slot ^ 1);
+      next = (next & ~(7u << (3 * depth))) | ((uint32_t)(slot + 1) << (3 * depth));
+      const int land = jump_target(cur, d);
+      captured |= 1u << step_target(cur, d);
+      visited |= 1u << land;
+      path |= (uint64_t)land << (5 * depth);
+      depth++;
+      next &= ~(7u << (3 * depth));
+      cur = land;
+    }
+  }
+  return count;
+}
+
+// All capture sequences of the position, origins ascending.  Returns the number visited.
 template <class Visit>
 B2P_HD int for_each_capture(const Pos &p, const JumpMasks &m, Visit &&visit) {
   uint32_t cap[4];
   capture_origins(p, m, cap);
   uint32_t origins = cap[0] | cap[1] | cap[2] | cap[3];
   int count = 0;
-  while (origins) {
+  bool stopped = false;
+  while (origins && !stopped) {
     const int o = lowbit(origins);
     origins &= origins - 1;
-    const bool king = (p.kings >> o) & 1u;
-    int cur = o, depth = 0;
-    uint32_t next = 0;       // next slot to try at each depth
-    uint32_t visited = 0;    // landing squares of the current sequence
-    uint32_t captured = 0;
-    uint64_t path = 0;
-    for (;;) {
-      // slots that can be hopped from `cur` (slot order = reference order for this piece type)
-      uint32_t v;
-      if (king) {
-        v = 0;
-        for (int d = 0; d < 4; d++) {
-          const int land = jump_target(cur, d);
-          const uint32_t ok = (m.j[d] >> cur) & 1u;
-          // land may be out of range when ok == 0; guard the shift
-          const uint32_t seen = ok ? ((visited >> (land & 31)) & 1u) : 0u;
-          v |= (ok & ~seen) << d;
-        }
-      } else {
-        v = ((m.j[1] >> cur) & 1u) | (((m.j[0] >> cur) & 1u) << 1);
-      }
-      const int ns = (int)((next >> (3 * depth)) & 7u);
-      const uint32_t todo = v & (0xFu << ns);
-      if (todo == 0) {
-        if (v == 0 && depth > 0) {
-          CaptureMove cm;
-          cm.from = o; cm.to = cur; cm.hops = depth; cm.captured = captured; cm.path = path;
-          count++;
-          if (visit(cm)) return count;
-        }
-        if (depth == 0) break;
-        // pop: undo the hop that led to `cur`
-        depth--;
-        const int slot = (int)((next >> (3 * depth)) & 7u) - 1;
-        const int d = king ? slot : (slot ^ 1);
-        const int parent = cur - (jump_target(cur, d) - cur);
-        visited &= ~(1u << cur);
-        captured &= ~(1u << step_target(parent, d));
-        path &= ~((uint64_t)31 << (5 * depth));
-        cur = parent;
-      } else {
-        const int slot = lowbit(todo);
-        const int d = king ? slot : (slot ^ 1);
-        next = (next & ~(7u << (3 * depth))) | ((uint32_t)(slot + 1) << (3 * depth));
-        const int land = jump_target(cur, d);
-        captured |= 1u << step_target(cur, d);
-        visited |= 1u << land;
-        path |= (uint64_t)land << (5 * depth);
-        depth++;
-        next &= ~(7u << (3 * depth));
-        cur = land;
-      }
-    }
+    count += for_each_capture_from(p, m, o, visit, stopped);
   }
   return count;
 }

@@ -241,10 +241,6 @@ cudaError_t launch_playout_lanes(const PlayoutParams &prm, KernelMode mode, int 
   return cudaErrorInvalidValue;
 }
 
-cudaError_t launch_playout_warp(const PlayoutParams &, KernelMode, int, cudaStream_t, LaunchInfo *) {
-  return cudaErrorNotSupported;  // warp-per-playout variant: see warp_kernel.cu (round 1: not built yet)
-}
-
 cudaError_t launch_genmoves(const uint4 *states, uint32_t n, int max_moves, unsigned long long *moves, uint8_t *counts,
                             cudaStream_t stream) {
   if (n == 0) return cudaSuccess;

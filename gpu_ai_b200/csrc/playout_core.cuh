@@ -150,69 +150,99 @@ B2P_HD void pick_multi_hop_capture(const Pos &p, const JumpMasks &jm, const uint
   }
 }
 
+// ---- one ply ----------------------------------------------------------------------------------
+// Everything a ply needs to know about the position, computed once: 4 step pre-images of the
+// empty set, 4 jump masks, capture origins per direction.
+struct PlyMasks {
+  uint32_t e[4];    // squares from which one step in direction d reaches an empty square
+  JumpMasks jm;
+  uint32_t cap[4];  // mover's squares with a first hop in direction d
+  bool capture;     // captures are mandatory (src/state.cu:239-245)
+};
+
+B2P_HD PlyMasks ply_masks(const Pos &p) {
+  PlyMasks m;
+  const uint32_t empty = ~(p.own | p.opp);
+  const uint32_t ownK = p.own & p.kings;
+  m.e[0] = stepDL(empty); m.e[1] = stepDR(empty); m.e[2] = stepUL(empty); m.e[3] = stepUR(empty);
+  m.jm.j[0] = stepDL(p.opp & m.e[0]);
+  m.jm.j[1] = stepDR(p.opp & m.e[1]);
+  m.jm.j[2] = stepUL(p.opp & m.e[2]);
+  m.jm.j[3] = stepUR(p.opp & m.e[3]);
+  m.cap[0] = p.own & m.jm.j[0];
+  m.cap[1] = p.own & m.jm.j[1];
+  m.cap[2] = ownK & m.jm.j[2];
+  m.cap[3] = ownK & m.jm.j[3];
+  m.capture = (m.cap[0] | m.cap[1] | m.cap[2] | m.cap[3]) != 0;
+  return m;
+}
+
+// Direct moves and single-hop captures share one branch-free path (four origin masks -> popc ->
+// rank -> k-th bit): the warp stays converged whether or not a lane must capture.
+// Returns the number of legal moves (0: the mover is stuck; outputs untouched).
+template <int ORDER>
+B2P_HD int pick_single_hop(const Pos &p, const PlyMasks &m, uint32_t turn, uint32_t r, uint32_t &from, uint32_t &to,
+                           uint32_t &captured) {
+  const uint32_t ownK = p.own & p.kings;
+  const bool capture = m.capture;
+  uint32_t a[4];
+  if (ORDER == kOrderCanonical) {
+    // reference slot order at one origin: capturing man UL,UR (left first); everything else UR,UL,DR,DL
+    const uint32_t men = ~p.kings;
+    const uint32_t c0 = (m.cap[1] & men) | (m.cap[0] & p.kings), c1 = (m.cap[0] & men) | (m.cap[1] & p.kings);
+    a[0] = capture ? c0 : (p.own & m.e[0]);
+    a[1] = capture ? c1 : (p.own & m.e[1]);
+  } else {
+    a[0] = capture ? m.cap[0] : (p.own & m.e[0]);
+    a[1] = capture ? m.cap[1] : (p.own & m.e[1]);
+  }
+  a[2] = capture ? m.cap[2] : (ownK & m.e[2]);
+  a[3] = capture ? m.cap[3] : (ownK & m.e[3]);
+  const int n0 = popc(a[0]), n1 = popc(a[1]), n2 = popc(a[2]);
+  const int n = n0 + n1 + n2 + popc(a[3]);
+  if (n == 0) return 0;
+  int k = (int)mulhi(r, (uint32_t)n);
+  int sel;
+  if (ORDER == kOrderCanonical) {
+    if (turn) k = n - 1 - k;
+    sel = select_origin_major(a, k);
+  } else {
+    sel = select_dir_major(a, n0, n1, n2, k);
+  }
+  const int o = sel & 31;
+  int d = sel >> 5;
+  if (ORDER == kOrderCanonical && capture && !((p.kings >> o) & 1u)) d ^= 1;
+  const int mid = step_target(o, d);
+  from = 1u << o;
+  to = 1u << (capture ? jump_target(o, d) : mid);
+  captured = capture ? (1u << mid) : 0u;
+  return n;
+}
+
+B2P_HD void finish_ply(Game &g, bool capture, uint32_t from, uint32_t to, uint32_t captured) {
+  g.msc = capture ? 0u : g.msc + 1u;
+  Pos q = g.pos;
+  apply_move(q, from, to, captured);
+  g.pos = flip(q);
+  g.turn ^= 1u;
+}
+
 // One ply with a uniformly random legal move chosen by the 32-bit draw r:
 // rank j = mulhi32(r, n) in the list order ORDER (bitboard.cuh).  Returns kRunning, or the
 // winner when the game is over BEFORE a move is made: -1 if msc >= 50 (the draw test wins
 // over "no moves", src/state.cpp:20-23), else the player who is not to move.
-//
-// Direct moves and single-hop captures share one branch-free path (four origin masks ->
-// popc -> rank -> k-th bit): the warp stays converged whether or not a lane must capture.
 template <int ORDER>
 B2P_HD int random_ply(Game &g, uint32_t r) {
   if (g.msc >= kDrawPlies) return -1;
   const Pos p = g.pos;
-  const uint32_t empty = ~(p.own | p.opp);
-  const uint32_t ownK = p.own & p.kings;
-  // squares from which one step in direction d reaches an empty square
-  const uint32_t e0 = stepDL(empty), e1 = stepDR(empty), e2 = stepUL(empty), e3 = stepUR(empty);
-  JumpMasks jm;
-  jm.j[0] = stepDL(p.opp & e0);
-  jm.j[1] = stepDR(p.opp & e1);
-  jm.j[2] = stepUL(p.opp & e2);
-  jm.j[3] = stepUR(p.opp & e3);
-  uint32_t cap[4] = {p.own & jm.j[0], p.own & jm.j[1], ownK & jm.j[2], ownK & jm.j[3]};
-  const bool capture = (cap[0] | cap[1] | cap[2] | cap[3]) != 0;
+  const PlyMasks m = ply_masks(p);
   uint32_t from, to, captured;
-  if (capture && any_second_hop(p, jm, cap)) {
-    pick_multi_hop_capture(p, jm, cap, r, ORDER == kOrderCanonical && g.turn != 0, from, to, captured);
+  if (m.capture && any_second_hop(p, m.jm, m.cap)) {
+    pick_multi_hop_capture(p, m.jm, m.cap, r, ORDER == kOrderCanonical && g.turn != 0, from, to, captured);
   } else {
-    uint32_t a[4];
-    if (ORDER == kOrderCanonical) {
-      // reference slot order at one origin: capturing man UL,UR (left first); everything else UR,UL,DR,DL
-      const uint32_t men = ~p.kings;
-      const uint32_t c0 = (cap[1] & men) | (cap[0] & p.kings), c1 = (cap[0] & men) | (cap[1] & p.kings);
-      a[0] = capture ? c0 : (p.own & e0);
-      a[1] = capture ? c1 : (p.own & e1);
-    } else {
-      a[0] = capture ? cap[0] : (p.own & e0);
-      a[1] = capture ? cap[1] : (p.own & e1);
-    }
-    a[2] = capture ? cap[2] : (ownK & e2);
-    a[3] = capture ? cap[3] : (ownK & e3);
-    const int n0 = popc(a[0]), n1 = popc(a[1]), n2 = popc(a[2]);
-    const int n = n0 + n1 + n2 + popc(a[3]);
-    if (n == 0) return (int)(g.turn ^ 1u);
-    int k = (int)mulhi(r, (uint32_t)n);
-    int sel;
-    if (ORDER == kOrderCanonical) {
-      if (g.turn) k = n - 1 - k;
-      sel = select_origin_major(a, k);
-    } else {
-      sel = select_dir_major(a, n0, n1, n2, k);
-    }
-    const int o = sel & 31;
-    int d = sel >> 5;
-    if (ORDER == kOrderCanonical && capture && !((p.kings >> o) & 1u)) d ^= 1;
-    const int mid = step_target(o, d);
-    from = 1u << o;
-    to = 1u << (capture ? jump_target(o, d) : mid);
-    captured = capture ? (1u << mid) : 0u;
+    if (pick_single_hop<ORDER>(p, m, g.turn, r, from, to, captured) == 0) return (int)(g.turn ^ 1u);
   }
-  g.msc = capture ? 0u : g.msc + 1u;
-  Pos q = p;
-  apply_move(q, from, to, captured);
-  g.pos = flip(q);
-  g.turn ^= 1u;
+  finish_ply(g, m.capture, from, to, captured);
   return kRunning;
 }
 

@@ -175,3 +175,38 @@ def test_full_size_properties(engine):
     assert np.array_equal(w3, w)
     w4, _, _, _ = engine.run_packed(st, key=2, order=ORDER_FAST)
     assert 0.5 < (w4 == w).mean() < 0.95
+
+
+# ---- warp-per-playout scheduling (B2P_SCHED_WARP) gives the same answers ------------------------------------
+@pytest.mark.parametrize("name", ["leaves", "synth"])
+@pytest.mark.parametrize("tag,mode,order", [("rc", MODE_RANDOM, ORDER_CANONICAL), ("rf", MODE_RANDOM, ORDER_FAST),
+                                            ("h", MODE_HEURISTIC, ORDER_CANONICAL)])
+def test_warp_scheduler_equals_golden(engine, golden, name, tag, mode, order):
+    import gpu_ai_b200 as b
+    st = golden[name + "_states"]
+    w, p, f, c = engine.run_packed(st, reps=2, key=12345, pid_base=1000, mode=mode, order=order, sched=b.SCHED_WARP,
+                                   want_plies=True, want_final=True)
+    assert np.array_equal(w, golden["%s_%s_winners" % (name, tag)])
+    assert np.array_equal(p, golden["%s_%s_plies" % (name, tag)])
+    assert np.array_equal(f, golden["%s_%s_final" % (name, tag)])
+    assert np.array_equal(c, golden["%s_%s_counters" % (name, tag)])
+
+
+@pytest.mark.parametrize("mode,order", [(MODE_RANDOM, ORDER_FAST), (MODE_HEURISTIC, ORDER_CANONICAL)])
+def test_warp_scheduler_equals_thread_scheduler(engine, mode, order):
+    import gpu_ai_b200 as b
+    st = np.concatenate([engine.gen_leaves(60000, key=21), fast_synthetic(20000, 23)])
+    a = engine.run_packed(st, key=3, mode=mode, order=order, sched=b.SCHED_THREAD, want_plies=True, want_final=True)
+    c = engine.run_packed(st, key=3, mode=mode, order=order, sched=b.SCHED_WARP, want_plies=True, want_final=True)
+    for x, y in zip(a, c):
+        assert np.array_equal(x, y)
+    # AUTO routes small batches to the warp kernel and large ones to the lane kernel: same answers either way
+    d = engine.run_packed(st[:500], key=3, mode=mode, order=order, sched=b.SCHED_AUTO, want_plies=True, want_final=True)
+    assert np.array_equal(d[0], a[0][:500]) and np.array_equal(d[1], a[1][:500])
+
+
+def test_warp_scheduler_truncated(engine, golden):
+    import gpu_ai_b200 as b
+    w, p, f, c = engine.run_packed(golden["synth_states"], key=12345, max_plies=5, sched=b.SCHED_WARP, want_plies=True, want_final=True)
+    assert np.array_equal(w, golden["synth_cut5_winners"])
+    assert np.array_equal(f, golden["synth_cut5_final"])

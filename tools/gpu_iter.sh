@@ -23,3 +23,16 @@ if [ "$2" == "extras" ]; then
    timeout 120 oracle/_ref/run_ai_ref -m playout_test -n 100000 -1 device_multiple -2 device_heuristic) 2>&1 | tee $OUT/run_ai_ref.txt | tail -40
 fi
 ls -la $OUT
+if [ "$2" == "sched" ] || [ "$3" == "sched" ]; then
+  echo "== thread vs warp scheduling"; timeout 600 python tools/sched_compare.py 2>&1 | tee $OUT/sched_compare.jsonl
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:playout_warp -s 2 -c 1 -f -o $OUT/prof_warp \
+    python - > $OUT/prof_warp_run.log 2>&1 <<PY
+import torch, gpu_ai_b200 as b
+eng=b.Engine(devices=[0]); dev=torch.device("cuda",0); N=1<<17
+s=torch.empty((N,4),dtype=torch.int32,device=dev); eng.gen_leaves_device(N,s.data_ptr(),key=2016)
+w=torch.empty(N,dtype=torch.int8,device=dev); c=torch.zeros(4,dtype=torch.int64,device=dev)
+for i in range(4):
+    eng.run_packed_device(s.data_ptr(),N,reps=1,key=i,mode=b.MODE_RANDOM,sched=b.SCHED_WARP,order=b.ORDER_FAST,d_winners=w.data_ptr(),d_counters=c.data_ptr(),stream=0)
+torch.cuda.synchronize()
+PY
+fi
