@@ -308,6 +308,15 @@ def main():
         out["e2e"] = {"value": n * world * k / dt, "unit": "playouts/s", "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": n,
                       "ms_per_call": 1e3 * dt / k, "host_input_bytes_per_step": 776 * n,
                       "api": "b2p_run_states776(host State[776 B] x n) -> int32 PlayerId[n]; pack + H2D + kernel + D2H timed"}
+        # the same call on 16-byte packed leaves (what a caller that keeps leaves packed would pay)
+        for _ in range(2):
+            eng.run_packed(packed, reps=1, key=1, mode=mode_i, order=order)
+        t_start = time.perf_counter()
+        for i in range(k):
+            eng.run_packed(packed, reps=1, key=2 + i, mode=mode_i, order=order)
+        dtp = sharding.max_over_ranks(time.perf_counter() - t_start, dev)
+        out["e2e_packed"] = {"value": n * world * k / dtp, "unit": "playouts/s", "ms_per_call": 1e3 * dtp / k,
+                             "api": "b2p_run_packed(host b2p_state16 x n) -> int8 winners + counters"}
         del s776
 
     # ---- CPU baseline on this box's host cores (rank 0, N = 1 only) --------------------------------------------

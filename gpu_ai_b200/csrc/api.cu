@@ -16,6 +16,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -38,11 +39,12 @@ struct Device {
   int id = -1;
   int sm_count = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t aux[4] = {nullptr, nullptr, nullptr, nullptr};  // chunk pipeline of b2p_run_states776
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   Buffer d_states, d_winners, d_plies, d_final, d_moves, d_counts, d_misc;
   Buffer h_states, h_winners, h_misc;  // pinned staging
-  unsigned int *d_next_ring = nullptr;  // 64 work-queue heads, rotated per launch
-  unsigned ring_pos = 0;
+  unsigned int *d_next_ring = nullptr;  // kRing work-queue heads, rotated per launch
+  unsigned ring_pos = 0;  // advanced under the caller's serialisation (one caller per context)
 };
 
 }  // namespace
@@ -94,11 +96,8 @@ void release(Buffer &b) {
   b.cap = 0;
 }
 
-unsigned int *next_slot(Device &d) {
-  unsigned int *p = d.d_next_ring + (d.ring_pos & 63u);
-  d.ring_pos++;
-  return p;
-}
+constexpr unsigned kRing = 256;
+unsigned int *next_slot(Device &d) { return d.d_next_ring + (d.ring_pos++ % kRing); }
 
 // B2P_SCHED_AUTO: warp-per-playout only pays below the batch size at which thread-per-playout
 // fills the machine's latency budget (measured on B200, profiles/: see DESIGN.md 4.5)
@@ -121,24 +120,34 @@ bool mode_to_kernel(int mode, int order, KernelMode *out) {
 constexpr size_t kStateBytes = 776, kItemBytes = 12, kTurnOff = 768, kMscOff = 772;
 constexpr size_t kMoveBytes = 38;
 
+// Branch-free: per dark square one 8-byte load (occupied @0, type @4) and one 4-byte load (owner @8);
+// type/owner only count where `occupied` is set (State::move leaves stale fields in vacated squares).
 inline void pack_one(const unsigned char *s, b2p_state16 *o) {
-  uint32_t p1 = 0, p2 = 0, k = 0;
-  for (int i = 0; i < 32; i++) {
-    const int r = i >> 2, c = 2 * (i & 3) + ((r & 1) ^ 1);
-    const unsigned char *q = s + kItemBytes * (size_t)(r * 8 + c);
-    if (!q[0]) continue;  // BoardItem::occupied; stale type/owner of vacated squares are ignored
-    int32_t type, owner;
-    std::memcpy(&type, q + 4, 4);
-    std::memcpy(&owner, q + 8, 4);
-    if (owner == 0) p1 |= 1u << i;
-    else p2 |= 1u << i;
-    if (type == 1) k |= 1u << i;
+  uint32_t occ = 0, p2 = 0, k = 0;
+#pragma GCC unroll 8
+  for (int r = 0; r < 8; r++) {
+    const unsigned char *row = s + 8 * kItemBytes * (size_t)r + kItemBytes * (size_t)((r & 1) ^ 1);
+#pragma GCC unroll 4
+    for (int j = 0; j < 4; j++) {
+      const unsigned char *q = row + 2 * kItemBytes * (size_t)j;
+      uint64_t w;
+      uint32_t owner;
+      std::memcpy(&w, q, 8);
+      std::memcpy(&owner, q + 8, 4);
+      const uint32_t oc = (uint32_t)(w & 0xFFu) != 0u;  // BoardItem::occupied
+      const uint32_t ty = (uint32_t)(w >> 32) == 1u;    // CHECKER_KING
+      const uint32_t ow = owner != 0u;                  // PLAYER_2
+      const int i = r * 4 + j;
+      occ |= oc << i;
+      p2 |= (oc & ow) << i;
+      k |= (oc & ty) << i;
+    }
   }
   int32_t turn;
   uint32_t msc;
   std::memcpy(&turn, s + kTurnOff, 4);
   std::memcpy(&msc, s + kMscOff, 4);
-  o->p1 = p1;
+  o->p1 = occ & ~p2;
   o->p2 = p2;
   o->kings = k;
   o->meta = (turn == 1 ? 1u : 0u) | (std::min<uint32_t>(msc, 0xFFFFFFu) << 8);
@@ -217,7 +226,7 @@ int b2p_create(b2p_ctx **out, const int *device_ids, int n_dev, uint64_t seed) {
     if ((e = cudaSetDevice(d.id)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, d.id)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreate(&d.ev0)) != cudaSuccess || (e = cudaEventCreate(&d.ev1)) != cudaSuccess ||
-        (e = cudaMalloc(&d.d_next_ring, 64 * sizeof(unsigned int))) != cudaSuccess) {
+        (e = cudaMalloc(&d.d_next_ring, kRing * sizeof(unsigned int))) != cudaSuccess) {
       ctx->devs.push_back(d);
       b2p_destroy(ctx);
       return fail(nullptr, B2P_ECUDA, std::string("b2p_create: ") + cudaGetErrorString(e));
@@ -228,6 +237,8 @@ int b2p_create(b2p_ctx **out, const int *device_ids, int n_dev, uint64_t seed) {
       return fail(nullptr, B2P_ENODEV, std::string("b2p_create: device ") + prop.name + " is not sm_100 class; the kernels are built for sm_100a only");
     }
     d.sm_count = prop.multiProcessorCount;
+    for (cudaStream_t &a : d.aux)
+      if (cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking) != cudaSuccess) a = nullptr;
     ctx->devs.push_back(d);
   }
   *out = ctx;
@@ -244,6 +255,8 @@ void b2p_destroy(b2p_ctx *ctx) {
     if (d.d_next_ring) cudaFree(d.d_next_ring);
     if (d.ev0) cudaEventDestroy(d.ev0);
     if (d.ev1) cudaEventDestroy(d.ev1);
+    for (cudaStream_t a : d.aux)
+      if (a) cudaStreamDestroy(a);
     if (d.stream) cudaStreamDestroy(d.stream);
   }
   delete ctx;
@@ -472,6 +485,14 @@ int b2p_run_states776(b2p_ctx *ctx, const void *states, size_t n, int mode, int 
   const int G = (int)std::min<size_t>(ctx->devs.size(), n);
   const unsigned char *src = (const unsigned char *)states;
   const KernelMode km = mode == B2P_MODE_HEURISTIC ? kHeuristic : kRandomFast;
+
+  // Chunk pipeline: host threads pack 776 B -> 16 B straight into pinned staging (48x less PCIe
+  // traffic than the reference's raw State copy); as soon as a chunk is packed its H2D copy,
+  // kernel and D2H copy are queued on one of the device's streams, so the GPU work of chunk c
+  // hides behind the packing of chunk c+1.  Playout ids are global, so chunking changes nothing.
+  struct Chunk { int g; size_t lo, len; };
+  std::vector<Chunk> chunks;
+  const size_t kChunk = n <= (1u << 16) ? n : (1u << 15);
   for (int g = 0; g < G; g++) {
     Device &d = ctx->devs[g];
     const Shard sh = shard_of(n, g, G);
@@ -483,34 +504,67 @@ int b2p_run_states776(b2p_ctx *ctx, const void *states, size_t n, int mode, int 
     if ((rc = ensure(ctx, d.d_states, nl * sizeof(b2p_state16), false))) return rc;
     if ((rc = ensure(ctx, d.d_winners, nl, false))) return rc;
     if ((rc = ensure(ctx, d.h_winners, nl, true))) return rc;
-    // 776 B -> 16 B on the host, straight into pinned staging: 48x less PCIe traffic than the reference
-    b2p_state16 *stage = (b2p_state16 *)d.h_states.ptr;
-    parallel_for(nl, 8192, [&](size_t lo, size_t hi) {
-      for (size_t i = lo; i < hi; i++) pack_one(src + kStateBytes * (sh.lo + i), stage + i);
-    });
-    B2P_CUDA(ctx, cudaMemcpyAsync(d.d_states.ptr, stage, nl * sizeof(b2p_state16), cudaMemcpyHostToDevice, d.stream));
-    PlayoutParams prm;
-    std::memset(&prm, 0, sizeof prm);
-    prm.states = reinterpret_cast<const uint4 *>(d.d_states.ptr);
-    prm.n = (uint32_t)nl;
-    prm.total = (uint32_t)nl;
-    prm.rep_stride = n;
-    prm.key = key;
-    prm.pid_base = sh.lo;
-    prm.max_plies = -1;
-    prm.winners = (int8_t *)d.d_winners.ptr;
-    prm.next = next_slot(d);
-    cudaError_t e = use_warp_kernel(sched, prm.total, km) ? launch_playout_warp(prm, km, d.sm_count, d.stream, nullptr)
-                                                      : launch_playout_lanes(prm, km, d.sm_count, d.stream, nullptr);
-    if (e != cudaSuccess) return fail(ctx, B2P_ECUDA, std::string("playout launch: ") + cudaGetErrorString(e));
-    ctx->launches++;
-    B2P_CUDA(ctx, cudaMemcpyAsync(d.h_winners.ptr, d.d_winners.ptr, nl, cudaMemcpyDeviceToHost, d.stream));
+    for (size_t lo = 0; lo < nl; lo += kChunk) chunks.push_back({g, lo, std::min(kChunk, nl - lo)});
   }
+  // interleave devices so that every GPU gets work early
+  std::stable_sort(chunks.begin(), chunks.end(), [](const Chunk &a, const Chunk &b) { return a.lo < b.lo; });
+
+  std::atomic<size_t> next_chunk{0};
+  std::mutex enqueue_mu;
+  std::string err;
+  auto worker = [&]() {
+    for (;;) {
+      const size_t c = next_chunk.fetch_add(1);
+      if (c >= chunks.size()) return;
+      const Chunk ch = chunks[c];
+      Device &d = ctx->devs[ch.g];
+      const Shard sh = shard_of(n, ch.g, G);
+      b2p_state16 *stage = (b2p_state16 *)d.h_states.ptr + ch.lo;
+      const unsigned char *from = src + kStateBytes * (sh.lo + ch.lo);
+      for (size_t i = 0; i < ch.len; i++) pack_one(from + kStateBytes * i, stage + i);
+      std::lock_guard<std::mutex> lock(enqueue_mu);
+      if (!err.empty()) return;
+      cudaStream_t st = d.aux[c % 4] ? d.aux[c % 4] : d.stream;
+      cudaError_t e = cudaSetDevice(d.id);
+      if (e == cudaSuccess)
+        e = cudaMemcpyAsync((b2p_state16 *)d.d_states.ptr + ch.lo, stage, ch.len * sizeof(b2p_state16), cudaMemcpyHostToDevice, st);
+      if (e == cudaSuccess) {
+        PlayoutParams prm;
+        std::memset(&prm, 0, sizeof prm);
+        prm.states = reinterpret_cast<const uint4 *>((b2p_state16 *)d.d_states.ptr + ch.lo);
+        prm.n = (uint32_t)ch.len;
+        prm.total = (uint32_t)ch.len;
+        prm.rep_stride = n;
+        prm.key = key;
+        prm.pid_base = sh.lo + ch.lo;
+        prm.max_plies = -1;
+        prm.winners = (int8_t *)d.d_winners.ptr + ch.lo;
+        prm.next = next_slot(d);
+        e = use_warp_kernel(sched, n, km) ? launch_playout_warp(prm, km, d.sm_count, st, nullptr)
+                                          : launch_playout_lanes(prm, km, d.sm_count, st, nullptr);
+        ctx->launches++;
+      }
+      if (e == cudaSuccess)
+        e = cudaMemcpyAsync((int8_t *)d.h_winners.ptr + ch.lo, (int8_t *)d.d_winners.ptr + ch.lo, ch.len, cudaMemcpyDeviceToHost, st);
+      if (e != cudaSuccess) err = std::string("b2p_run_states776 pipeline: ") + cudaGetErrorString(e);
+    }
+  };
+  {
+    const unsigned hw = std::thread::hardware_concurrency();
+    const size_t workers = std::min<size_t>(std::min<size_t>(hw ? hw : 1, 32), chunks.size());
+    std::vector<std::thread> th;
+    for (size_t t = 1; t < workers; t++) th.emplace_back(worker);
+    worker();
+    for (auto &t : th) t.join();
+  }
+  if (!err.empty()) return fail(ctx, B2P_ECUDA, err);
   for (int g = 0; g < G; g++) {
     Device &d = ctx->devs[g];
     const Shard sh = shard_of(n, g, G);
     const size_t nl = sh.hi - sh.lo;
     B2P_CUDA(ctx, cudaSetDevice(d.id));
+    for (cudaStream_t a : d.aux)
+      if (a) B2P_CUDA(ctx, cudaStreamSynchronize(a));
     B2P_CUDA(ctx, cudaStreamSynchronize(d.stream));
     const int8_t *w = (const int8_t *)d.h_winners.ptr;
     parallel_for(nl, 1 << 16, [&](size_t lo, size_t hi) {

@@ -30,6 +30,14 @@
 #define B2P_HD inline
 #endif
 
+// keep a float in a register: stops the compiler from sinking a division into a loop that
+// only uses its result conditionally
+#if defined(__CUDA_ARCH__)
+#define B2P_PIN_FLOAT(x) asm volatile("" : "+f"(x))
+#else
+#define B2P_PIN_FLOAT(x) ((void)(x))
+#endif
+
 namespace b2p {
 
 // ---- portable bit primitives ------------------------------------------------------------

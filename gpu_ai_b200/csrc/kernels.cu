@@ -127,17 +127,8 @@ __global__ void __launch_bounds__(kLaneBlock) playout_lanes_kernel(const Playout
         res = random_ply<kOrderFast>(probe, 0u);
         if (res == kRunning) res = 3;  // marker: unfinished
       } else if (kHeur) {
-        int cached = -1;
-        Philox4 nb;
-        nb.v[0] = nb.v[1] = nb.v[2] = nb.v[3] = 0;
-        res = heuristic_ply(g, [&](int i) {
-          const int b = i >> 2;
-          if (b != cached) {
-            nb = philox_block(prm.key, pid, kDomainNoise | ((uint32_t)b << 8), ply);
-            cached = b;
-          }
-          return gauss_lookup(s_gauss, pick4(nb, i & 3));
-        });
+        res = heuristic_ply(g, [&](int b) { return philox_block(prm.key, pid, kDomainNoise | ((uint32_t)b << 8), ply); },
+                            [&](uint32_t r) { return gauss_lookup(s_gauss, r); });
       } else {
         res = random_ply<kOrder>(g, pick4(rnd, q));
       }

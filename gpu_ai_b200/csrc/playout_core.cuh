@@ -93,15 +93,34 @@ B2P_HD void pick_multi_hop_capture(const Pos &p, const JumpMasks &jm, const uint
   const uint32_t anyJ = jm.j[0] | jm.j[1] | jm.j[2] | jm.j[3];
   const uint32_t land_king = jumpUR(cap[0] & K) | jumpUL(cap[1] & K) | jumpDR(cap[2]) | jumpDL(cap[3]);
   if (land_king & anyJ) {
-    const int n = for_each_capture(p, jm, [](const CaptureMove &) { return false; });
+    // one DFS pass: remember the first kLeafBuf sequences, pick by index afterwards (a second
+    // walk is needed only when the chosen index lies beyond the buffer -- practically never)
+    constexpr int kLeafBuf = 12;
+    uint32_t buf_captured[kLeafBuf];
+    uint16_t buf_from_to[kLeafBuf];
+    int seen = 0;
+    const int n = for_each_capture(p, jm, [&](const CaptureMove &cm) {
+      if (seen < kLeafBuf) {
+        buf_captured[seen] = cm.captured;
+        buf_from_to[seen] = (uint16_t)(cm.from | (cm.to << 5));
+      }
+      seen++;
+      return false;
+    });
     int k = (int)mulhi(r, (uint32_t)n);
     if (reverse) k = n - 1 - k;
-    from = to = captured = 0;
-    for_each_capture(p, jm, [&](const CaptureMove &cm) {
-      if (k-- != 0) return false;
-      from = 1u << cm.from; to = 1u << cm.to; captured = cm.captured;
-      return true;
-    });
+    if (k < kLeafBuf) {
+      from = 1u << (buf_from_to[k] & 31);
+      to = 1u << (buf_from_to[k] >> 5);
+      captured = buf_captured[k];
+    } else {
+      from = to = captured = 0;
+      for_each_capture(p, jm, [&](const CaptureMove &cm) {
+        if (k-- != 0) return false;
+        from = 1u << cm.from; to = 1u << cm.to; captured = cm.captured;
+        return true;
+      });
+    }
     return;
   }
   const uint32_t E0 = jm.j[0], E1 = jm.j[1];
@@ -252,57 +271,147 @@ B2P_HD int random_ply(Game &g, uint32_t r) {
 //   weight = float(my + 3*promoted) / float(opp - value of captured pieces) + noise
 // and the FIRST maximum (strict '>') is played.  Material is recomputed from the board
 // (popc) instead of being carried incrementally -- same value by construction.
-// NoiseFn: float noise(int canonical_index).
-template <class NoiseFn>
-B2P_HD int heuristic_ply(Game &g, NoiseFn &&noise) {
+//
+// Candidate i (canonical list position) of the ply takes its noise from word i&3 of noise block
+// i>>2 (philox.cuh).  NoiseBlock: Philox4 block(int b);  Gauss: float gauss(uint32_t r).
+//
+// The common case -- only direct moves, none of them crowning (all candidates share one base
+// weight) -- never identifies the individual moves: it scans the noise stream block by block
+// (one Philox call per 4 candidates, the same blocks at the same time in every lane of a warp),
+// keeps the first maximum of base + noise, and only then maps the winning index to a move.
+struct HeurBest {
+  float w;
+  int idx;
+};
+
+B2P_HD bool heur_better(float w, int idx, const HeurBest &b) { return w > b.w || (w == b.w && idx < b.idx); }
+
+template <class NoiseBlock, class Gauss>
+B2P_HD int heuristic_ply(Game &g, NoiseBlock &&noise_block, Gauss &&gauss) {
   if (g.msc >= kDrawPlies) return -1;
   const Pos p = g.pos;
-  const JumpMasks jm = jump_masks(p);
-  uint32_t a[4];
-  capture_origins(p, jm, a);
+  const PlyMasks m = ply_masks(p);
   const uint32_t my = material(p.own, p.kings), his = material(p.opp, p.kings);
   const uint32_t ownMen = p.own & ~p.kings;
   const bool rev = g.turn != 0;  // canonical index = n-1-normalised index for PLAYER_2
   uint32_t from = 0, to = 0, captured = 0;
-  float best = -__builtin_inff();
-  if ((a[0] | a[1] | a[2] | a[3]) != 0) {
-    const int n = for_each_capture(p, jm, [](const CaptureMove &) { return false; });
-    int i = 0;
-    for_each_capture(p, jm, [&](const CaptureMove &cm) {
-      const uint32_t promo = (((ownMen >> cm.from) & 1u) && cm.to >= 28) ? 3u : 0u;
-      const uint32_t loss = (uint32_t)(popc(cm.captured) + 3 * popc(cm.captured & p.kings));
-      const float w = (float)(my + promo) / (float)(his - loss) + noise(rev ? n - 1 - i : i);
-      // first maximum in canonical order: ascending scan keeps '>', the reversed scan (PLAYER_2) takes '>='
-      if (rev ? (w >= best) : (w > best)) { best = w; from = 1u << cm.from; to = 1u << cm.to; captured = cm.captured; }
-      i++;
+  HeurBest best;
+  best.w = -__builtin_inff();
+  best.idx = 0x7fffffff;
+  int cached = -1;
+  Philox4 nb;
+  nb.v[0] = nb.v[1] = nb.v[2] = nb.v[3] = 0;
+  auto noise = [&](int idx) {
+    const int b = idx >> 2;
+    if (b != cached) { nb = noise_block(b); cached = b; }
+    const int q = idx & 3;
+    uint32_t r = nb.v[0];
+    r = q == 1 ? nb.v[1] : r;
+    r = q == 2 ? nb.v[2] : r;
+    r = q == 3 ? nb.v[3] : r;
+    return gauss(r);
+  };
+  if (m.capture && any_second_hop(p, m.jm, m.cap)) {
+    // multi-hop sequences: one register-DFS pass buffers the sequences, then they are scored in
+    // list order (the canonical index of PLAYER_2 needs the total count first)
+    constexpr int kLeafBuf = 12;
+    uint32_t buf_captured[kLeafBuf];
+    uint16_t buf_from_to[kLeafBuf];
+    int seen = 0;
+    const int n = for_each_capture(p, m.jm, [&](const CaptureMove &cm) {
+      if (seen < kLeafBuf) {
+        buf_captured[seen] = cm.captured;
+        buf_from_to[seen] = (uint16_t)(cm.from | (cm.to << 5));
+      }
+      seen++;
       return false;
     });
-    g.msc = 0;
+    auto score = [&](int i, int f, int t, uint32_t cap) {
+      const int idx = rev ? n - 1 - i : i;
+      const uint32_t promo = (((ownMen >> f) & 1u) && t >= 28) ? 3u : 0u;
+      const uint32_t loss = (uint32_t)(popc(cap) + 3 * popc(cap & p.kings));
+      const float w = (float)(my + promo) / (float)(his - loss) + noise(idx);
+      if (heur_better(w, idx, best)) { best.w = w; best.idx = idx; from = 1u << f; to = 1u << t; captured = cap; }
+    };
+    for (int i = 0; i < n && i < kLeafBuf; i++) score(i, buf_from_to[i] & 31, buf_from_to[i] >> 5, buf_captured[i]);
+    if (n > kLeafBuf) {
+      int i = 0;
+      for_each_capture(p, m.jm, [&](const CaptureMove &cm) {
+        if (i >= kLeafBuf) score(i, cm.from, cm.to, cm.captured);
+        i++;
+        return false;
+      });
+    }
   } else {
-    step_origins(p, a);
+    // one list entry per (origin, slot): same four masks as the random path, canonical slot order
+    const uint32_t ownK = p.own & p.kings;
+    const uint32_t men = ~p.kings;
+    uint32_t a[4];
+    a[0] = m.capture ? ((m.cap[1] & men) | (m.cap[0] & p.kings)) : (p.own & m.e[0]);
+    a[1] = m.capture ? ((m.cap[0] & men) | (m.cap[1] & p.kings)) : (p.own & m.e[1]);
+    a[2] = m.capture ? m.cap[2] : (ownK & m.e[2]);
+    a[3] = m.capture ? m.cap[3] : (ownK & m.e[3]);
     const int n = popc(a[0]) + popc(a[1]) + popc(a[2]) + popc(a[3]);
     if (n == 0) return (int)(g.turn ^ 1u);
-    const float plain = (float)my / (float)his, crowned = (float)(my + 3u) / (float)his;
-    uint32_t origins = a[0] | a[1] | a[2] | a[3];
-    int i = 0;
-    while (origins) {
-      const int o = lowbit(origins);
-      origins &= origins - 1;
-      const bool man = (ownMen >> o) & 1u;
-      for (int d = 0; d < 4; d++) {
-        if (!((a[d] >> o) & 1u)) continue;
-        const int t = step_target(o, d);
-        const float w = ((man && t >= 28) ? crowned : plain) + noise(rev ? n - 1 - i : i);
-        if (rev ? (w >= best) : (w > best)) { best = w; from = 1u << o; to = 1u << t; }
-        i++;
+    if (!m.capture) {
+      // direct moves: one base weight; the few crowning moves (men one step from the far row) are
+      // marked by their canonical index so that the scan below never has to identify a move
+      float base = (float)my / (float)his, crowned = (float)(my + 3u) / (float)his;
+      B2P_PIN_FLOAT(base);
+      B2P_PIN_FLOAT(crowned);
+      const uint32_t cr0 = a[0] & ownMen & 0x0F000000u, cr1 = a[1] & ownMen & 0x0F000000u;
+      uint64_t crown_idx = 0;
+      for (uint32_t cr = cr0 | cr1; cr; cr &= cr - 1) {
+        const int o = lowbit(cr);
+        const uint32_t below = (1u << o) - 1u;
+        const int first = popc(a[0] & below) + popc(a[1] & below) + popc(a[2] & below) + popc(a[3] & below);
+        if ((cr0 >> o) & 1u) crown_idx |= 1ull << (rev ? n - 1 - first : first);
+        const int second = first + (int)((a[0] >> o) & 1u);
+        if ((cr1 >> o) & 1u) crown_idx |= 1ull << (rev ? n - 1 - second : second);
+      }
+      for (int b = 0; 4 * b < n; b++) {
+        const Philox4 blk = noise_block(b);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int q = 0; q < 4; q++) {
+          const int idx = 4 * b + q;
+          const float w = (((crown_idx >> idx) & 1ull) ? crowned : base) + gauss(blk.v[q]);
+          if (idx < n && w > best.w) { best.w = w; best.idx = idx; }
+        }
+      }
+    } else {
+      // single-hop captures: few candidates, each with its own weight; walk them origin by origin
+      int i = 0;
+      for (uint32_t origins = a[0] | a[1] | a[2] | a[3]; origins; origins &= origins - 1) {
+        const int o = lowbit(origins);
+        const bool man = (ownMen >> o) & 1u;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int slot = 0; slot < 4; slot++) {
+          if (!((a[slot] >> o) & 1u)) continue;
+          const int d = man ? (slot ^ 1) : slot;
+          const int mid = step_target(o, d);
+          const uint32_t promo = (man && jump_target(o, d) >= 28) ? 3u : 0u;
+          const uint32_t loss = ((p.kings >> mid) & 1u) ? 4u : 1u;
+          const int idx = rev ? n - 1 - i : i;
+          const float w = (float)(my + promo) / (float)(his - loss) + noise(idx);
+          if (heur_better(w, idx, best)) { best.w = w; best.idx = idx; }
+          i++;
+        }
       }
     }
-    g.msc++;
+    const int sel = select_origin_major(a, rev ? n - 1 - best.idx : best.idx);
+    const int o = sel & 31;
+    int d = sel >> 5;
+    if (m.capture && ((ownMen >> o) & 1u)) d ^= 1;
+    const int mid = step_target(o, d);
+    from = 1u << o;
+    to = 1u << (m.capture ? jump_target(o, d) : mid);
+    captured = m.capture ? (1u << mid) : 0u;
   }
-  Pos q = p;
-  apply_move(q, from, to, captured);
-  g.pos = flip(q);
-  g.turn ^= 1u;
+  finish_ply(g, m.capture, from, to, captured);
   return kRunning;
 }
 

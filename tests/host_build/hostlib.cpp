@@ -51,15 +51,13 @@ void hb_playouts_batch(const uint32_t *packed, size_t n, uint32_t reps, uint64_t
       if (max_plies >= 0 && (int)ply >= max_plies) {
         // stopped early: still report a finished game as finished (oracle does the same)
         Game probe = g;
-        res = mode == 1 ? heuristic_ply(probe, [](int) { return 0.0f; }) : random_ply<kOrderFast>(probe, 0);
+        res = random_ply<kOrderFast>(probe, 0);
         if (res == kRunning) break;
         break;
       }
       if (mode == 1) {
-        res = heuristic_ply(g, [&](int i) {
-          Philox4 b = philox_block(key, pid, kDomainNoise | ((uint32_t)(i >> 2) << 8), ply);
-          return gauss_sigma(b.v[i & 3]);
-        });
+        res = heuristic_ply(g, [&](int b) { return philox_block(key, pid, kDomainNoise | ((uint32_t)b << 8), ply); },
+                            [](uint32_t r) { return gauss_sigma(r); });
       } else {
         Philox4 b = philox_block(key, pid, kDomainRandom, ply >> 2);
         uint32_t r = b.v[ply & 3];

@@ -210,3 +210,21 @@ def test_warp_scheduler_truncated(engine, golden):
     w, p, f, c = engine.run_packed(golden["synth_states"], key=12345, max_plies=5, sched=b.SCHED_WARP, want_plies=True, want_final=True)
     assert np.array_equal(w, golden["synth_cut5_winners"])
     assert np.array_equal(f, golden["synth_cut5_final"])
+
+
+def test_run_states776_bit_exact_through_the_chunk_pipeline(port):
+    """The reference-facing entry point (pack -> chunked H2D/kernel/D2H pipeline) is itself replayable:
+    call c of a context uses key = seed + c * 0x9E3779B97F4A7C15 and global leaf indices as playout ids."""
+    import gpu_ai_b200 as b
+    eng = b.Engine(devices=1, seed=4711)
+    st = eng.gen_leaves(200003, key=2016)          # > 65536: exercises the multi-chunk path, ragged last chunk
+    s776 = port.unpack776(st)
+    for call in range(2):
+        key = (4711 + call * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+        res = eng.run_states776(s776, mode=b.MODE_RANDOM)
+        ow, _, _, _ = port.playouts(st, key=key, order=ORDER_FAST)
+        assert np.array_equal(res, ow.astype(np.int32))
+    res = eng.run_states776(s776[:3000], mode=b.MODE_HEURISTIC, sched=b.SCHED_AUTO)   # small batch -> warp kernel
+    key = (4711 + 2 * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+    ow, _, _, _ = port.playouts(st[:3000], key=key, mode=MODE_HEURISTIC)
+    assert np.array_equal(res, ow.astype(np.int32))
