@@ -247,37 +247,35 @@ struct CaptureMove {
   uint64_t path;      // landing square of hop k in bits [5k, 5k+5)
 };
 
+// single-bit mask of square s, 0 when s is off the board (s may be negative or >= 32)
+B2P_HD uint32_t bit_or_zero(int s) { return (uint32_t)(1ull << (s & 63)); }
+
 // Sequences that start on square `o` (which must hold a piece of the mover with a first hop).
 // Calls visit(const CaptureMove&) for each complete sequence in reference order; visit returns
 // true to stop (then `stopped` is set).  Returns the number of sequences visited.
+//
+// The king's "never land twice on the same square" rule (src/state.cu:134-139) is kept in the
+// jump masks themselves: entering a landing square removes, in a working copy of the four masks,
+// the (at most four) hops that end on it; leaving it restores them.  Expanding a node is then
+// four bit extractions instead of four visited-set tests.
 template <class Visit>
 B2P_HD int for_each_capture_from(const Pos &p, const JumpMasks &m, int o, Visit &&visit, bool &stopped) {
   int count = 0;
   const bool king = (p.kings >> o) & 1u;
   int cur = o, depth = 0;
-  uint32_t next = 0;       // next slot to try at each depth
-  uint32_t visited = 0;    // landing squares of the current sequence
+  uint32_t next = 0;       // next slot to try at each depth (3 bits per depth)
   uint32_t captured = 0;
   uint64_t path = 0;
+  uint32_t w0 = m.j[0], w1 = m.j[1], w2 = m.j[2], w3 = m.j[3];  // working masks (kings)
   for (;;) {
     // slots that can be hopped from `cur` (slot order = reference order for this piece type)
     uint32_t v;
-    if (king) {
-      v = 0;
-      for (int d = 0; d < 4; d++) {
-        const int land = jump_target(cur, d);
-        const uint32_t ok = (m.j[d] >> cur) & 1u;
-        // land may be out of range when ok == 0; guard the shift
-        const uint32_t seen = ok ? ((visited >> (land & 31)) & 1u) : 0u;
-        v |= (ok & ~seen) << d;
-      }
-    } else {
-      v = ((m.j[1] >> cur) & 1u) | (((m.j[0] >> cur) & 1u) << 1);
-    }
+    if (king) v = ((w0 >> cur) & 1u) | (((w1 >> cur) & 1u) << 1) | (((w2 >> cur) & 1u) << 2) | (((w3 >> cur) & 1u) << 3);
+    else v = ((m.j[1] >> cur) & 1u) | (((m.j[0] >> cur) & 1u) << 1);
     const int ns = (int)((next >> (3 * depth)) & 7u);
     const uint32_t todo = v & (0xFu << ns);
     if (todo == 0) {
-      if (v == 0 && depth > 0) {
+      if (ns == 0 && depth > 0) {  // nothing was ever hoppable from here: a complete sequence
         CaptureMove cm;
         cm.from = o; cm.to = cur; cm.hops = depth; cm.captured = captured; cm.path = path;
         count++;
@@ -289,7 +287,12 @@ B2P_HD int for_each_capture_from(const Pos &p, const JumpMasks &m, int o, Visit 
       const int slot = (int)((next >> (3 * depth)) & 7u) - 1;
       const int d = king ? slot : (slot ^ 1);
       const int parent = cur - (jump_target(cur, d) - cur);
-      visited &= ~(1u << cur);
+      if (king) {
+        w0 |= m.j[0] & bit_or_zero(cur - 9);
+        w1 |= m.j[1] & bit_or_zero(cur - 7);
+        w2 |= m.j[2] & bit_or_zero(cur + 7);
+        w3 |= m.j[3] & bit_or_zero(cur + 9);
+      }
       captured &= ~(1u << step_target(parent, d));
       path &= ~((uint64_t)31 << (5 * depth));
       cur = parent;
@@ -299,7 +302,12 @@ B2P_HD int for_each_capture_from(const Pos &p, const JumpMasks &m, int o, Visit 
       next = (next & ~(7u << (3 * depth))) | ((uint32_t)(slot + 1) << (3 * depth));
       const int land = jump_target(cur, d);
       captured |= 1u << step_target(cur, d);
-      visited |= 1u << land;
+      if (king) {
+        w0 &= ~bit_or_zero(land - 9);
+        w1 &= ~bit_or_zero(land - 7);
+        w2 &= ~bit_or_zero(land + 7);
+        w3 &= ~bit_or_zero(land + 9);
+      }
       path |= (uint64_t)land << (5 * depth);
       depth++;
       next &= ~(7u << (3 * depth));
