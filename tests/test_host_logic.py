@@ -57,3 +57,32 @@ def test_ply_step_equals_port_large(hostbuild, port, mode, order):
 
 def test_leafgen_equals_golden(hostbuild, golden):
     assert np.array_equal(hostbuild.gen_leaves(4096, key=2016), golden["leaves_states"])
+
+
+def test_playouts_from_the_initial_position(hostbuild, port):
+    """D_start (BASELINE configs[0]): many playouts of the one starting state -- long games (mean ~68 plies),
+    every rule exercised from a reachable root; bit-exact against the port in both orders."""
+    from oracle.pyoracle import START_PACKED
+    st = np.tile(START_PACKED, (1, 1))
+    for order in (ORDER_CANONICAL, ORDER_FAST):
+        a = hostbuild.playouts(st, reps=20000, key=5, order=order, want_final=True)
+        b = port.playouts(st, reps=20000, key=5, order=order, want_final=True)
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+    assert 60 < a[1].mean() < 76   # SURVEY section 6: 68.4 plies per playout from the start
+
+
+def test_bitboard_movelists_hypothesis(hostbuild, port):
+    """property test: arbitrary piece placements (any overlap-free p1/p2/kings words, any turn/msc)"""
+    from hypothesis import given, settings, strategies as st32
+    word = st32.integers(min_value=0, max_value=2**32 - 1)
+
+    @settings(max_examples=300, deadline=None)
+    @given(word, word, word, st32.integers(0, 1), st32.integers(0, 60))
+    def check(a, b, k, turn, msc):
+        state = np.array([[a & ~b, b & ~a, k, turn | (msc << 8)]], dtype=np.uint32)
+        m1, c1 = hostbuild.genmoves(state, 100)
+        m2, c2 = port.genmoves(state, 100)
+        assert c1[0] == c2[0] and np.array_equal(m1, m2)
+
+    check()
