@@ -84,10 +84,22 @@ constexpr uint32_t kOddRows = 0xF0F0F0F0u;
 constexpr uint32_t kEvenNotCol7 = 0x07070707u;
 constexpr uint32_t kOddNotCol0 = 0xE0E0E0E0u;
 
+// x >> S for a compile-time S.  Experiment B2P_SHR_ON_FMA issues it as IMAD.HI (x * 2^(32-S) >> 32)
+// to move work from the saturated ALU pipe (ncu: 85 %) to the FMA pipe (20 %).  Measured on B200
+// (profiles/r01i_ab.txt): IMAD.HI is half rate (32/clk/SM) and the kernel gets 2.4 % SLOWER -- off.
+template <int S>
+B2P_HD uint32_t shr(uint32_t x) {
+#if defined(__CUDA_ARCH__) && defined(B2P_SHR_ON_FMA)
+  return __umulhi(x, 1u << (32 - S));
+#else
+  return x >> S;
+#endif
+}
+
 B2P_HD uint32_t stepUR(uint32_t x) { return ((x & kEvenNotCol7) << 5) | ((x & kOddRows) << 4); }
 B2P_HD uint32_t stepUL(uint32_t x) { return ((x & kEvenRows) << 4) | ((x & kOddNotCol0) << 3); }
-B2P_HD uint32_t stepDR(uint32_t x) { return ((x & kEvenNotCol7) >> 3) | ((x & kOddRows) >> 4); }
-B2P_HD uint32_t stepDL(uint32_t x) { return ((x & kEvenRows) >> 4) | ((x & kOddNotCol0) >> 5); }
+B2P_HD uint32_t stepDR(uint32_t x) { return shr<3>(x & kEvenNotCol7) | shr<4>(x & kOddRows); }
+B2P_HD uint32_t stepDL(uint32_t x) { return shr<4>(x & kEvenRows) | shr<5>(x & kOddNotCol0); }
 
 // two steps in one direction (a jump landing): +9 / +7 / -7 / -9, legal while col+-2 stays on
 // the board (i%4 <= 2 going right, i%4 >= 1 going left)
@@ -95,8 +107,8 @@ constexpr uint32_t kNotRight2 = 0x77777777u;
 constexpr uint32_t kNotLeft2 = 0xEEEEEEEEu;
 B2P_HD uint32_t jumpUR(uint32_t x) { return (x & kNotRight2) << 9; }
 B2P_HD uint32_t jumpUL(uint32_t x) { return (x & kNotLeft2) << 7; }
-B2P_HD uint32_t jumpDR(uint32_t x) { return (x & kNotRight2) >> 7; }
-B2P_HD uint32_t jumpDL(uint32_t x) { return (x & kNotLeft2) >> 9; }
+B2P_HD uint32_t jumpDR(uint32_t x) { return shr<7>(x & kNotRight2); }
+B2P_HD uint32_t jumpDL(uint32_t x) { return shr<9>(x & kNotLeft2); }
 
 // per-square scalars: target index of one step / one jump from square s in direction d
 B2P_HD int step_target(int s, int d) {
@@ -188,6 +200,12 @@ B2P_HD Pos flip(const Pos &p) {
 
 // ---- selecting the k-th set bit ---------------------------------------------------------------
 B2P_HD int select_bit(uint32_t m, int k) {
+#if defined(__CUDA_ARCH__) && !defined(B2P_NO_PEEL_SELECT)
+  // the masks are sparse (a handful of origins per direction): clearing k low bits beats the
+  // 5-step popcount search even at the warp's worst lane (+2 % playouts/s, profiles/r01i_ab.txt)
+  for (; k > 0; k--) m &= m - 1;
+  return lowbit(m);
+#endif
   int r = 0, c;
   c = popc(m & 0xFFFFu); if (k >= c) { k -= c; m >>= 16; r = 16; }
   c = popc(m & 0xFFu);   if (k >= c) { k -= c; m >>= 8;  r += 8; }

@@ -37,6 +37,15 @@ __device__ __forceinline__ void one_round(uint32_t (&x)[kChains]) {
       asm volatile("brev.b32 %0, %0;" : "+r"(a));
     } else if (WHICH == 7) {
       asm volatile("bfind.u32 %0, %0;" : "+r"(a));
+    } else if (WHICH == 9) {
+      asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(a) : "r"(b));
+    } else if (WHICH == 10) {
+      // right shift on the FMA pipe (x >> 4 == mulhi(x, 2^28)) interleaved with LOP3 on the ALU pipe
+      if (i & 1) asm volatile("mul.hi.u32 %0, %0, 0x10000000;" : "+r"(a));
+      else asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a) : "r"(b), "r"(c));
+    } else if (WHICH == 11) {
+      if (i & 1) asm volatile("shr.u32 %0, %0, 4;" : "+r"(a));
+      else asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a) : "r"(b), "r"(c));
     } else if (WHICH == 8) {
       // 3:1 LOP3:IMAD, the mix of the playout kernel
       if ((i & 3) == 3) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a) : "r"(b), "r"(c));
@@ -82,6 +91,9 @@ cudaError_t launch_microbench(int which, int iters, int sm_count, uint32_t *sink
     case 6: return run<6>(iters, grid, sink, stream);
     case 7: return run<7>(iters, grid, sink, stream);
     case 8: return run<8>(iters, grid, sink, stream);
+    case 9: return run<9>(iters, grid, sink, stream);
+    case 10: return run<10>(iters, grid, sink, stream);
+    case 11: return run<11>(iters, grid, sink, stream);
   }
   return cudaErrorInvalidValue;
 }

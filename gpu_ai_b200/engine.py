@@ -20,7 +20,8 @@ class B2PError(RuntimeError):
 
 
 def lib_path():
-    return os.path.join(_HERE, "libb2p.so")
+    # B2P_LIB_PATH: load an experiment build (make -C gpu_ai_b200/csrc variant ...) instead of the shipped library
+    return os.environ.get("B2P_LIB_PATH") or os.path.join(_HERE, "libb2p.so")
 
 
 class DevInfo(C.Structure):

@@ -137,7 +137,8 @@ int b2p_expand_move(b2p_move_t move, void *move38_out);
 
 /* ---- measurement helpers ------------------------------------------------------------------------
  * Dependency-light integer-pipe microbenchmarks that freeze the INT32 roofline denominator
- * (SURVEY.md 8d).  which: 0 LOP3, 1 IADD3, 2 SHF, 3 POPC, 4 IMAD, 5 LOP3+IMAD mix, 6 BREV.
+ * (SURVEY.md 8d).  which: 0 LOP3, 1 IADD3, 2 SHF, 3 POPC, 4 IMAD, 5 LOP3+IMAD 1:1, 6 BREV, 7 FLO, 8 LOP3+IMAD 3:1,
+ * 9 IMAD.HI, 10 LOP3 + mul.hi-as-shift, 11 LOP3 + SHF.R.
  * Returns thread-level ops per second over the whole chip. */
 int b2p_microbench(b2p_ctx *ctx, int dev_index, int which, int iters, double *thread_ops_per_s, double *ms);
 /* number of kernels this context has launched so far (bench.py reports it as gpu_launches) */

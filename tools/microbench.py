@@ -7,7 +7,7 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import gpu_ai_b200 as b  # noqa: E402
 
-NAMES = ["LOP3", "IADD3", "SHF", "POPC", "IMAD", "LOP3+IMAD 1:1", "BREV", "FLO(bfind)", "LOP3+IMAD 3:1"]
+NAMES = ["LOP3", "IADD3", "SHF", "POPC", "IMAD", "LOP3+IMAD 1:1", "BREV", "FLO(bfind)", "LOP3+IMAD 3:1", "IMAD.HI (mul.hi)", "LOP3 + mul.hi-as-shift 1:1", "LOP3 + SHF.R 1:1"]
 eng = b.Engine(devices=1)
 info = eng.device_info(0)
 res = {"gpu": info["name"], "sms": info["sm_count"], "clock_khz_max": info["clock_khz"], "rates": {}}
