@@ -10,8 +10,9 @@
 //   block(key, pid, domain, b) = philox4x32_10(ctr = {pid_lo, pid_hi, b, domain}, key = {key_lo, key_hi})
 //   draw t of a stream         = block(key, pid, domain, t >> 2)[t & 3]
 //   random playout, ply p      : move index = mulhi32(draw p of domain 0, n_moves)
-//   heuristic playout          : candidate i of ply p gets noise from
-//                                block(key, pid, kDomainNoise | (i >> 2) << 8, p)[i & 3]
+//   heuristic playout          : candidate i of ply p gets noise from the 16-bit half (i & 1) of word
+//                                (i >> 1) & 3 of block(key, pid, kDomainNoise | (i >> 3) << 8, p):
+//                                one block serves 8 candidates
 //   leaf generation            : domain 2; draw 0 -> prefix length 1 + mulhi32(r, 100),
 //                                draw 1 + p -> move index of prefix ply p
 #pragma once

@@ -272,8 +272,9 @@ B2P_HD int random_ply(Game &g, uint32_t r) {
 // and the FIRST maximum (strict '>') is played.  Material is recomputed from the board
 // (popc) instead of being carried incrementally -- same value by construction.
 //
-// Candidate i (canonical list position) of the ply takes its noise from word i&3 of noise block
-// i>>2 (philox.cuh).  NoiseBlock: Philox4 block(int b);  Gauss: float gauss(uint32_t r).
+// Candidate i (canonical list position) of the ply takes its noise from 16-bit half i&1 of word
+// (i>>1)&3 of noise block i>>3 (philox.cuh): 8 candidates per Philox call.
+// NoiseBlock: Philox4 block(int b);  Gauss: float gauss(uint32_t h16).
 //
 // The common case -- only direct moves, none of them crowning (all candidates share one base
 // weight) -- never identifies the individual moves: it scans the noise stream block by block
@@ -302,14 +303,14 @@ B2P_HD int heuristic_ply(Game &g, NoiseBlock &&noise_block, Gauss &&gauss) {
   Philox4 nb;
   nb.v[0] = nb.v[1] = nb.v[2] = nb.v[3] = 0;
   auto noise = [&](int idx) {
-    const int b = idx >> 2;
+    const int b = idx >> 3;
     if (b != cached) { nb = noise_block(b); cached = b; }
-    const int q = idx & 3;
+    const int q = (idx >> 1) & 3;
     uint32_t r = nb.v[0];
     r = q == 1 ? nb.v[1] : r;
     r = q == 2 ? nb.v[2] : r;
     r = q == 3 ? nb.v[3] : r;
-    return gauss(r);
+    return gauss((idx & 1) ? r >> 16 : r & 0xFFFFu);
   };
   if (m.capture && any_second_hop(p, m.jm, m.cap)) {
     // multi-hop sequences: one register-DFS pass buffers the sequences, then they are scored in
@@ -369,14 +370,15 @@ B2P_HD int heuristic_ply(Game &g, NoiseBlock &&noise_block, Gauss &&gauss) {
         const int second = first + (int)((a[0] >> o) & 1u);
         if ((cr1 >> o) & 1u) crown_idx |= 1ull << (rev ? n - 1 - second : second);
       }
-      for (int b = 0; 4 * b < n; b++) {
+      for (int b = 0; 8 * b < n; b++) {
         const Philox4 blk = noise_block(b);
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-        for (int q = 0; q < 4; q++) {
-          const int idx = 4 * b + q;
-          const float w = (((crown_idx >> idx) & 1ull) ? crowned : base) + gauss(blk.v[q]);
+        for (int q = 0; q < 8; q++) {
+          const int idx = 8 * b + q;
+          const uint32_t h = (q & 1) ? blk.v[q >> 1] >> 16 : blk.v[q >> 1] & 0xFFFFu;
+          const float w = (((crown_idx >> idx) & 1ull) ? crowned : base) + gauss(h);
           if (idx < n && w > best.w) { best.w = w; best.idx = idx; }
         }
       }

@@ -14,9 +14,9 @@
 
 using namespace b2p;
 
-static float gauss_sigma(uint32_t r) {
-  uint32_t i = r >> 22;
-  float frac = (float)(r & 0x3FFFFFu) * (1.0f / 4194304.0f);
+static float gauss_sigma(uint32_t h) {
+  uint32_t i = (h >> 6) & 1023u;
+  float frac = (float)(h & 63u) * (1.0f / 64.0f);
   float lo, hi;
   std::memcpy(&lo, &b2p_gauss_table_bits[i], 4);
   std::memcpy(&hi, &b2p_gauss_table_bits[i + 1], 4);
