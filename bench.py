@@ -55,6 +55,9 @@ def parse():
 
 # ---- clocks ---------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock, power and throttle reasons DURING the timed region.  NVML in a thread (10 ms period, no
+    process start-up latency, so even a 100 ms region gets samples); falls back to the nvidia-smi loop of
+    the profiling recipe when pynvml is unavailable."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -62,8 +65,28 @@ class ClockSampler:
         self.gpu = gpu_index
         self.rows = []
         self.proc = None
+        self.nvml = None
+        self.samples = []
+        self.stop_flag = threading.Event()
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # honour CUDA_VISIBLE_DEVICES: map the CUDA ordinal to the NVML device through its UUID/PCI bus id
+            import torch
+            bus = torch.cuda.get_device_properties(self.gpu)
+            handle = None
+            try:
+                handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(bus.uuid)).encode())
+            except Exception:
+                handle = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.nvml = (pynvml, handle)
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
                                           "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -72,13 +95,42 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def _poll(self):
+        nv, h = self.nvml
+        while not self.stop_flag.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append((sm, mx, pw, rs))
+            except Exception:
+                pass
+            time.sleep(0.01)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
     def stop(self):
+        if self.nvml:
+            self.stop_flag.set()
+            self.thread.join(timeout=2)
+            nv = self.nvml[0]
+            bits = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                    "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                    "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                    "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+            reasons = sorted(k for k, b in bits.items() if any(s[3] & b for s in self.samples))
+            sm = [s[0] for s in self.samples]
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(s[1] for s in self.samples) if sm else None,
+                    "power_w_max": max(s[2] for s in self.samples) if sm else None, "samples": len(sm), "reasons": reasons,
+                    "source": "nvml, 10 ms period, during the timed region"}
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML and no nvidia-smi"], "samples": 0}
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -100,7 +152,8 @@ class ClockSampler:
                 if f[5 + k].lower().startswith("active"):
                     reasons.add(nme)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons),
+                "source": "nvidia-smi -lms 100"}
 
 
 # ---- CPU baseline ------------------------------------------------------------------------------------
@@ -251,9 +304,19 @@ def main():
     k_ms = float(np.mean(kernel_ms))
     plies_per_launch = plies_per_playout * n * reps
     achieved = plies_per_launch * W_PLY / (k_ms * 1e-3)
+    # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this very
+    # command (profiles/traffic.json, written by tools/extract_traffic.py); null when the configuration differs
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tj = json.load(f)
+        if (tj["leaves"], tj["reps"], tj["mode"], tj["order"]) == (n, reps, args.mode, args.order):
+            traffic = tj["dram_bytes_per_launch"]
+    except (OSError, KeyError, ValueError):
+        pass
     roofline = {
         "bound": "int32_issue", "achieved": achieved / 1e12, "peak": peak_alu / 1e12, "unit": "T thread-op/s",
-        "frac": achieved / peak_alu, "traffic": None,
+        "frac": achieved / peak_alu, "traffic": traffic,
         "peak_source": "b2p_microbench LOP3 (ALU pipe) measured live on this GPU; LOP3+IMAD dual-pipe %.2f T/s" % (peak_mix / 1e12),
         "model": "W_ply = 180 INT32 thread-ops/ply (SURVEY.md 8d) x %.2f plies/playout counted by the kernel" % plies_per_playout,
         "plies_per_s": plies_per_launch / (k_ms * 1e-3), "kernel_ms": k_ms,

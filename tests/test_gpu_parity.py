@@ -228,3 +228,48 @@ def test_run_states776_bit_exact_through_the_chunk_pipeline(port):
     key = (4711 + 2 * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
     ow, _, _, _ = port.playouts(st[:3000], key=key, mode=MODE_HEURISTIC)
     assert np.array_equal(res, ow.astype(np.int32))
+
+
+# ---- boundary behaviour: threading and errors -------------------------------------------------------------------
+def test_two_contexts_from_two_threads(port):
+    """Two MCTSPlayer workers call runPlayouts concurrently (src/player.cpp:119-150): contexts are independent."""
+    import threading
+    import gpu_ai_b200 as b
+    st = b.Engine(devices=1).gen_leaves(150000, key=3)
+    expect = {}
+    for key in (11, 22):
+        expect[key] = port.playouts(st[:20000], key=key, order=ORDER_FAST)[0]
+    out = {}
+
+    def work(key):
+        eng = b.Engine(devices=1, seed=key)
+        for _ in range(3):
+            w, _, _, _ = eng.run_packed(st, key=key, order=ORDER_FAST)
+        out[key] = w
+
+    th = [threading.Thread(target=work, args=(k,)) for k in (11, 22)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for key in (11, 22):
+        assert np.array_equal(out[key][:20000], expect[key])
+
+
+def test_errors_are_codes_not_crashes(engine):
+    import ctypes as C
+    import gpu_ai_b200 as b
+    st = engine.gen_leaves(16, key=1)
+    with pytest.raises(b.B2PError, match="unknown mode"):
+        engine.run_packed(st, mode=7)
+    with pytest.raises(b.B2PError):
+        engine.run_packed(st, reps=2 ** 31 - 1)                     # n * reps >= 2^31
+    with pytest.raises(b.B2PError):
+        engine.run_states776(np.zeros(776 * 4, np.uint8), mode=9)
+    lib = b.load_library()
+    assert lib.b2p_run_states776(None, None, 5, 0, 0, None) == -1     # B2P_EINVAL on a NULL context
+    assert lib.b2p_run_states776(engine.ctx, None, 5, 0, 0, None) == -1
+    assert b"NULL" in lib.b2p_last_error(engine.ctx)
+    with pytest.raises(b.B2PError, match="out of range"):
+        b.Engine(devices=[99])
+    # the context is still usable after errors
+    w, _, _, _ = engine.run_packed(st)
+    assert w.shape == (16,)
