@@ -16,6 +16,7 @@ from .engine import (  # noqa: F401
     SCHED_AUTO,
     SCHED_THREAD,
     SCHED_WARP,
+    Tree,
     lib_path,
     load_library,
 )
@@ -29,7 +30,7 @@ from .drivers import (  # noqa: F401
 )
 
 __all__ = [
-    "B2PError", "Engine", "load_library", "lib_path",
+    "B2PError", "Engine", "Tree", "load_library", "lib_path",
     "MODE_RANDOM", "MODE_HEURISTIC", "SCHED_THREAD", "SCHED_WARP", "SCHED_AUTO", "ORDER_CANONICAL", "ORDER_FAST",
     "PlayoutDriver", "DeviceSinglePlayoutDriver", "DeviceMultiplePlayoutDriver", "DeviceCoarsePlayoutDriver",
     "DeviceHeuristicPlayoutDriver", "getPlayoutDriver",

@@ -124,10 +124,8 @@ constexpr size_t kMoveBytes = 38;
 // type/owner only count where `occupied` is set (State::move leaves stale fields in vacated squares).
 inline void pack_one(const unsigned char *s, b2p_state16 *o) {
   uint32_t occ = 0, p2 = 0, k = 0;
-#pragma GCC unroll 8
   for (int r = 0; r < 8; r++) {
     const unsigned char *row = s + 8 * kItemBytes * (size_t)r + kItemBytes * (size_t)((r & 1) ^ 1);
-#pragma GCC unroll 4
     for (int j = 0; j < 4; j++) {
       const unsigned char *q = row + 2 * kItemBytes * (size_t)j;
       uint64_t w;

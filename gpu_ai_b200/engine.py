@@ -51,6 +51,16 @@ ABI = [
     ("b2p_expand_move", _INT, [_U64, _VP]),
     ("b2p_microbench", _INT, [_VP, _INT, _INT, _INT, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     ("b2p_launch_count", _U64, [_VP]),
+    ("b2p_tree_create", _INT, [C.POINTER(_VP), _VP]),
+    ("b2p_tree_destroy", None, [_VP]),
+    ("b2p_tree_select", _INT, [_VP, _U32, _VP, C.POINTER(_U32)]),
+    ("b2p_tree_update", _INT, [_VP, _VP, _U32, _U32]),
+    ("b2p_tree_best_move", _INT, [_VP, _INT, C.POINTER(_U64)]),
+    ("b2p_tree_move", _INT, [_VP, _U64]),
+    ("b2p_tree_info", _INT, [_VP, _VP]),
+    ("b2p_tree_root_moves", _INT, [_VP, _VP, _VP, _VP, _VP, _U32]),
+    ("b2p_tree_last_error", C.c_char_p, [_VP]),
+    ("b2p_tree_search", _INT, [_VP, _VP, _U32, C.c_double, _U32, C.c_float, _U32, _INT, _U64, C.POINTER(_U64)]),
 ]
 
 _lib = None
@@ -190,6 +200,71 @@ class Engine:
         ops, ms = C.c_double(), C.c_double()
         self._check(self.lib.b2p_microbench(self.ctx, dev_index, which, iters, C.byref(ops), C.byref(ms)))
         return ops.value, ms.value
+
+
+class TreeStats(C.Structure):
+    _fields_ = [("nodes", _U64), ("total_trials", _U64), ("wins_p1", _U64), ("wins_p2", _U64), ("root_children", _U32),
+                ("root_moves", _U32), ("root_state", _U32 * 4)]
+
+
+class Tree:
+    """b2p_tree: the packed-state counterpart of the reference's GameTree (src/mcts.hpp:12-64)."""
+
+    def __init__(self, root_state):
+        self.lib = load_library()
+        self.h = C.c_void_p()
+        root = np.ascontiguousarray(root_state, dtype=np.uint32).reshape(4)
+        if self.lib.b2p_tree_create(C.byref(self.h), _ptr(root)) != 0:
+            raise B2PError("b2p_tree_create failed")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.b2p_tree_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def _check(self, rc):
+        if rc != 0:
+            raise B2PError("b2p_tree error %d: %s" % (rc, self.lib.b2p_tree_last_error(self.h).decode()))
+
+    def select(self, trials):
+        out = np.empty((max(trials, 1), 4), dtype=np.uint32)
+        n = _U32()
+        self._check(self.lib.b2p_tree_select(self.h, trials, _ptr(out), C.byref(n)))
+        return out[: n.value]
+
+    def update(self, winners, reps=1):
+        w = np.ascontiguousarray(winners, dtype=np.int8)
+        self._check(self.lib.b2p_tree_update(self.h, _ptr(w), w.size // reps, reps))
+
+    def best_move(self, player):
+        m = _U64()
+        self._check(self.lib.b2p_tree_best_move(self.h, player, C.byref(m)))
+        return int(m.value)
+
+    def move(self, move):
+        self._check(self.lib.b2p_tree_move(self.h, int(move)))
+
+    def info(self):
+        st = TreeStats()
+        self._check(self.lib.b2p_tree_info(self.h, C.byref(st)))
+        return {"nodes": st.nodes, "total_trials": st.total_trials, "wins": (st.wins_p1, st.wins_p2),
+                "root_children": st.root_children, "root_moves": st.root_moves,
+                "root_state": np.array(list(st.root_state), dtype=np.uint32)}
+
+    def root_moves(self):
+        cap = 128
+        mv, tr = np.zeros(cap, np.uint64), np.zeros(cap, np.uint64)
+        w1, w2 = np.zeros(cap, np.uint64), np.zeros(cap, np.uint64)
+        n = self.lib.b2p_tree_root_moves(self.h, _ptr(mv), _ptr(tr), _ptr(w1), _ptr(w2), cap)
+        return mv[:n], tr[:n], w1[:n], w2[:n]
+
+    def search(self, engine, iterations=0, seconds=0.0, initial_batch=50, scale=0.02, reps=1, mode=MODE_RANDOM, key=1):
+        played = _U64()
+        rc = self.lib.b2p_tree_search(engine.ctx, self.h, iterations, seconds, initial_batch, scale, reps, mode, key, C.byref(played))
+        self._check(rc)
+        return int(played.value)
 
 
 # ---- converters (no context, no device) -------------------------------------------------------------

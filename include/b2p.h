@@ -144,6 +144,40 @@ int b2p_microbench(b2p_ctx *ctx, int dev_index, int which, int iters, double *th
 /* number of kernels this context has launched so far (bench.py reports it as gpu_launches) */
 uint64_t b2p_launch_count(const b2p_ctx *ctx);
 
+/* ---- search tree: the caller side of the path ----------------------------------------
+ * Replaces GameTree (src/mcts.hpp:12-64, src/mcts.cpp:11-191) decision for decision -- fed the same playout
+ * results it selects the same leaves in the same order -- on 16-byte packed states, writing leaves straight
+ * into the caller's buffer (no per-level vector<State> concatenation, src/mcts.cpp:144-156).  Host-side, like
+ * the reference's tree; no CUDA context needed except for b2p_tree_search. */
+typedef struct b2p_tree b2p_tree;
+typedef struct b2p_tree_stats {
+  uint64_t nodes;
+  uint64_t total_trials; /* GameTree::getTotalTrials of the root */
+  uint64_t wins_p1, wins_p2;
+  uint32_t root_children, root_moves;
+  b2p_state16 root_state;
+} b2p_tree_stats;
+
+int b2p_tree_create(b2p_tree **out, const b2p_state16 *root);            /* GameTree::GameTree(State) */
+void b2p_tree_destroy(b2p_tree *tree);
+/* GameTree::select (src/mcts.cpp:63-157): leaves_out needs room for `trials` states; *n_out = leaves written */
+int b2p_tree_select(b2p_tree *tree, uint32_t trials, b2p_state16 *leaves_out, uint32_t *n_out);
+/* GameTree::update (src/mcts.cpp:159-180).  winners: PlayerId per trial of the last select, n = its leaf count;
+ * reps > 1: `reps` playouts per selected leaf laid out [rep][leaf] exactly as b2p_run_packed returns them */
+int b2p_tree_update(b2p_tree *tree, const int8_t *winners, uint32_t n, uint32_t reps);
+int b2p_tree_best_move(const b2p_tree *tree, int player, b2p_move_t *move_out);   /* GameTree::getOptMove */
+int b2p_tree_move(b2p_tree *tree, b2p_move_t move);                      /* GameTree::move (subtree reuse) */
+int b2p_tree_info(const b2p_tree *tree, b2p_tree_stats *out);
+/* root move list with per-child statistics; returns the number of legal root moves */
+int b2p_tree_root_moves(const b2p_tree *tree, b2p_move_t *moves_out, uint64_t *trials_out, uint64_t *wins_p1_out,
+                        uint64_t *wins_p2_out, uint32_t capacity);
+const char *b2p_tree_last_error(const b2p_tree *tree);
+/* MCTSPlayer::worker (src/player.cpp:134-150) fused with the playout engine: select -> playouts -> update,
+ * batch = max(initial_batch, scale * leaf selections so far), `reps` playouts per selected leaf, until `iterations`
+ * rounds or `seconds` of wall clock (0 = unlimited on that axis; both 0 = nothing). */
+int b2p_tree_search(b2p_ctx *ctx, b2p_tree *tree, uint32_t iterations, double seconds, uint32_t initial_batch,
+                    float scale, uint32_t reps, int mode, uint64_t key, uint64_t *playouts_out);
+
 #ifdef __cplusplus
 }
 #endif

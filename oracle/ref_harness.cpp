@@ -16,6 +16,7 @@
 #include "heuristic.hpp"  // /root/reference/src
 #include "playout.hpp"    // /root/reference/src
 #include "genMovesTest.hpp"
+#include "mcts.hpp"        // /root/reference/src: GameTree
 
 #include <cmath>
 #include <cstddef>
@@ -274,5 +275,47 @@ int ref_host_driver_run(const uint32_t *packed, size_t n, int mode, int32_t *win
     return -1;
   }
 }
+
+// ---- the reference's GameTree (src/mcts.hpp, src/mcts.cpp), for pinning b2p_tree (tests/test_tree.py) ----
+struct RefTree {
+  std::shared_ptr<GameTree> tree;
+};
+
+void *ref_tree_create(const uint32_t packed_root[4]) {
+  RefTree *t = new RefTree();
+  t->tree = std::make_shared<GameTree>(unpack(packed_root));
+  return t;
+}
+
+void ref_tree_destroy(void *h) { delete (RefTree *)h; }
+
+size_t ref_tree_select(void *h, unsigned trials, uint32_t *packed_out) {
+  std::vector<State> leaves = ((RefTree *)h)->tree->select(trials);
+  for (size_t i = 0; i < leaves.size(); i++) pack(leaves[i], packed_out + 4 * i);
+  return leaves.size();
+}
+
+void ref_tree_update(void *h, const int8_t *winners, size_t n) {
+  std::vector<PlayerId> r(n);
+  for (size_t i = 0; i < n; i++) r[i] = (PlayerId)winners[i];
+  ((RefTree *)h)->tree->update(r);
+}
+
+uint64_t ref_tree_total(void *h) { return ((RefTree *)h)->tree->getTotalTrials(); }
+
+uint64_t ref_tree_best_move(void *h, int player) { return encode(((RefTree *)h)->tree->getOptMove((PlayerId)player)); }
+
+// GameTree::move with the move given as its compact record (matched against the root's own list)
+int ref_tree_move(void *h, uint64_t move) {
+  RefTree *t = (RefTree *)h;
+  for (const Move &m : t->tree->state.getMoves())
+    if (encode(m) == move) {
+      t->tree = t->tree->move(m);
+      return 0;
+    }
+  return -1;
+}
+
+void ref_tree_root_state(void *h, uint32_t packed_out[4]) { pack(((RefTree *)h)->tree->state, packed_out); }
 
 }  // extern "C"

@@ -273,3 +273,25 @@ def test_errors_are_codes_not_crashes(engine):
     # the context is still usable after errors
     w, _, _, _ = engine.run_packed(st)
     assert w.shape == (16,)
+
+
+# ---- next row: tree search fused with the playout engine ---------------------------------------------
+def test_tree_search_on_gpu(engine, port):
+    import gpu_ai_b200 as b
+    t = b.Tree(START_PACKED)
+    played = t.search(engine, iterations=20, initial_batch=200, scale=0.02, reps=8, key=5)
+    info = t.info()
+    assert played == info["total_trials"] and played >= 20 * 200 * 8  # batch never shrinks below initial_batch
+    assert info["wins"][0] + info["wins"][1] <= played
+    mv, tr, w1, w2 = t.root_moves()
+    assert len(mv) == 7 and tr.sum() == played               # every playout is accounted for at the root's children
+    best = t.best_move(0)
+    legal, cnt = port.genmoves(START_PACKED.reshape(1, 4), 64)
+    assert best in set(int(x) for x in legal[0, :cnt[0]])
+    # the search is deterministic for a given key
+    t2 = b.Tree(START_PACKED)
+    t2.search(engine, iterations=20, initial_batch=200, scale=0.02, reps=8, key=5)
+    assert np.array_equal(t2.root_moves()[1], tr) and np.array_equal(t2.root_moves()[2], w1)
+    # subtree reuse keeps the statistics of the chosen child
+    t.move(best)
+    assert t.info()["total_trials"] == int(tr[list(mv).index(best)])

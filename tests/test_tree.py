@@ -1,0 +1,115 @@
+"""CPU: b2p_tree (gpu_ai_b200/csrc/tree.cu) against the reference's own GameTree (src/mcts.cpp), SURVEY.md 8f-1.
+
+Both trees are driven with the same deterministic fake playout results (a hash of the leaf state), batch
+after batch; every batch of selected leaves, the trial totals, the chosen move and the re-rooted subtree
+must be identical.  The live comparison needs oracle/_ref (build container); the golden trace generated from
+it (tests/golden/tree_trace.npz, tools/make_tree_golden.py) travels to the GPU box."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from oracle.pyoracle import START_PACKED, make_state
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def fake_winners(leaves, salt):
+    """deterministic 'playout result' per leaf: -1 / 0 / 1 from a hash of the packed state"""
+    a = leaves.astype(np.uint64)
+    h = (a[:, 0] * np.uint64(0x9E3779B1) ^ a[:, 1] * np.uint64(0x85EBCA77) ^ a[:, 2] * np.uint64(0xC2B2AE3D) ^ a[:, 3] + np.uint64(salt))
+    h = (h ^ (h >> np.uint64(15))) * np.uint64(0x2545F491)
+    return ((h >> np.uint64(7)) % np.uint64(3)).astype(np.int8) - 1
+
+
+class RefTree:
+    def __init__(self, ref, root):
+        self.lib = ref.lib
+        self.lib.ref_tree_create.restype = C.c_void_p
+        self.lib.ref_tree_select.restype = C.c_size_t
+        self.lib.ref_tree_total.restype = C.c_uint64
+        self.lib.ref_tree_best_move.restype = C.c_uint64
+        r = np.ascontiguousarray(root, dtype=np.uint32)
+        self.h = C.c_void_p(self.lib.ref_tree_create(r.ctypes.data_as(C.c_void_p)))
+
+    def select(self, trials):
+        out = np.zeros((max(trials, 1), 4), dtype=np.uint32)
+        n = self.lib.ref_tree_select(self.h, C.c_uint(trials), out.ctypes.data_as(C.c_void_p))
+        return out[:n]
+
+    def update(self, winners):
+        w = np.ascontiguousarray(winners, dtype=np.int8)
+        self.lib.ref_tree_update(self.h, w.ctypes.data_as(C.c_void_p), C.c_size_t(w.size))
+
+    def total(self):
+        return int(self.lib.ref_tree_total(self.h))
+
+    def best_move(self, player):
+        return int(self.lib.ref_tree_best_move(self.h, player))
+
+    def move(self, m):
+        assert self.lib.ref_tree_move(self.h, C.c_uint64(m)) == 0
+
+    def root_state(self):
+        out = np.zeros(4, dtype=np.uint32)
+        self.lib.ref_tree_root_state(self.h, out.ctypes.data_as(C.c_void_p))
+        return out
+
+
+BATCHES = [50, 1, 2, 0, 7, 50, 257, 50, 50, 1000, 3, 50, 4000, 80, 80, 80, 513, 50, 50, 2000]
+
+
+def drive(tree, batches, salt, moves_after=(7, 14)):
+    """MCTSPlayer-like session: select/update rounds, two moves played in between (subtree reuse)"""
+    trace = []
+    for i, n in enumerate(batches):
+        leaves = np.array(tree.select(n), copy=True)
+        trace.append(leaves)
+        tree.update(fake_winners(leaves, salt + i) if len(leaves) else np.zeros(0, np.int8))
+        if i in moves_after:
+            root = tree.root_state() if hasattr(tree, "root_state") else tree.info()["root_state"]
+            m = tree.best_move(int(root[3] & 1))
+            trace.append(np.array([[m & 0xFFFFFFFF, m >> 32, 0, 0]], dtype=np.uint32))
+            tree.move(m)
+    return trace
+
+
+@pytest.mark.parametrize("name,root", [("start", START_PACKED),
+                                       ("endgame", make_state(p1_kings=[(2, 1)], p1_men=[(1, 4)], p2_men=[(5, 2), (6, 5)], p2_kings=[(7, 0)])),
+                                       ("captures", make_state(p1_men=[(2, 1), (2, 3), (1, 6)], p2_men=[(3, 2), (5, 4), (5, 6), (6, 1)], turn=0))])
+def test_tree_equals_reference_gametree_live(ref, name, root):
+    import gpu_ai_b200 as b
+    mine, theirs = b.Tree(root), RefTree(ref, root)
+    a = drive(mine, BATCHES, salt=11)
+    c = drive(theirs, BATCHES, salt=11)
+    assert len(a) == len(c)
+    for x, y in zip(a, c):
+        assert x.shape == y.shape and np.array_equal(x, y)
+    assert mine.info()["total_trials"] == theirs.total()
+
+
+def test_tree_equals_golden_trace():
+    import gpu_ai_b200 as b
+    g = np.load(os.path.join(ROOT, "tests", "golden", "tree_trace.npz"))
+    tree = b.Tree(g["root"])
+    trace = drive(tree, [int(x) for x in g["batches"]], salt=int(g["salt"]))
+    flat = np.concatenate([t for t in trace if len(t)])
+    assert np.array_equal(flat, g["flat"])
+    assert [len(t) for t in trace] == list(g["lengths"])
+    assert tree.info()["total_trials"] == int(g["total"])
+
+
+def test_tree_reps_and_errors():
+    import gpu_ai_b200 as b
+    t = b.Tree(START_PACKED)
+    leaves = t.select(50)
+    assert len(leaves) == 50
+    with pytest.raises(b.B2PError):
+        t.update(np.zeros(49, np.int8))                 # wrong result count (the reference asserts)
+    t.update(np.tile(fake_winners(leaves, 1), 4), reps=4)   # 4 playouts per selected leaf
+    assert t.info()["total_trials"] == 200
+    mv, tr, w1, w2 = t.root_moves()
+    assert len(mv) == 7 and tr.sum() == 200
+    with pytest.raises(b.B2PError):
+        t.move(0xFFFF)                                   # not a legal root move
