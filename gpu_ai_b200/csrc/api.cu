@@ -348,6 +348,7 @@ int b2p_run_packed_device(b2p_ctx *ctx, int dev_index, const b2p_state16 *d_stat
   B2P_CUDA(ctx, cudaSetDevice(d.id));
   cudaStream_t st = (cudaStream_t)cuda_stream;
   PlayoutParams prm;
+  std::memset(&prm, 0, sizeof prm);
   prm.states = reinterpret_cast<const uint4 *>(d_states);
   prm.n = (uint32_t)n;
   prm.total = (uint32_t)(n * reps);
@@ -437,6 +438,7 @@ int b2p_run_packed(b2p_ctx *ctx, const b2p_state16 *states, size_t n, uint32_t r
     B2P_CUDA(ctx, cudaMemcpyAsync(d.d_states.ptr, states + sh.lo, nl * sizeof(b2p_state16), cudaMemcpyHostToDevice, d.stream));
     B2P_CUDA(ctx, cudaMemsetAsync(d.d_misc.ptr, 0, 4 * sizeof(uint64_t), d.stream));
     PlayoutParams prm;
+    std::memset(&prm, 0, sizeof prm);
     prm.states = reinterpret_cast<const uint4 *>(d.d_states.ptr);
     prm.n = (uint32_t)nl;
     prm.total = (uint32_t)tl;
@@ -463,6 +465,60 @@ int b2p_run_packed(b2p_ctx *ctx, const b2p_state16 *states, size_t n, uint32_t r
     B2P_CUDA(ctx, cudaMemcpyAsync(d.h_misc.ptr, d.d_misc.ptr, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, d.stream));
   }
   // phase 2: wait and combine the per-device counters on the host ("host gather" of north_star)
+  for (int g = 0; g < G; g++) {
+    Device &d = ctx->devs[g];
+    B2P_CUDA(ctx, cudaSetDevice(d.id));
+    B2P_CUDA(ctx, cudaStreamSynchronize(d.stream));
+    if (counters_out)
+      for (int k = 0; k < 4; k++) counters_out[k] += ((const uint64_t *)d.h_misc.ptr)[k];
+  }
+  return B2P_OK;
+}
+
+// K playouts per leaf, win COUNTS per leaf back: what a tree search needs from a batch.
+// 16 B per leaf up, 8 B per leaf down, whatever `reps` is; the per-playout winners never leave the device.
+int b2p_run_counts(b2p_ctx *ctx, const b2p_state16 *states, size_t n, uint32_t reps, uint64_t key, uint64_t pid_base,
+                   int mode, int sched, int order, uint32_t *wins_out, uint64_t counters_out[4]) {
+  if (!ctx) return B2P_EINVAL;
+  if (counters_out) counters_out[0] = counters_out[1] = counters_out[2] = counters_out[3] = 0;
+  if (n == 0 || reps == 0) return B2P_OK;
+  if (!states || !wins_out) return fail(ctx, B2P_EINVAL, "NULL buffer");
+  KernelMode km;
+  if (!mode_to_kernel(mode, order, &km)) return fail(ctx, B2P_EINVAL, "unknown mode/order");
+  const int G = (int)std::min<size_t>(ctx->devs.size(), n);
+  for (int g = 0; g < G; g++) {
+    Device &d = ctx->devs[g];
+    const Shard sh = shard_of(n, g, G);
+    const size_t nl = sh.hi - sh.lo, tl = nl * reps;
+    if ((unsigned long long)tl >= (1ull << 31)) return fail(ctx, B2P_EINVAL, "per-device n*reps must be < 2^31");
+    B2P_CUDA(ctx, cudaSetDevice(d.id));
+    int rc;
+    if ((rc = ensure(ctx, d.d_states, nl * sizeof(b2p_state16), false))) return rc;
+    if ((rc = ensure(ctx, d.d_plies, nl * 2 * sizeof(uint32_t), false))) return rc;  // reused as the per-leaf count buffer
+    if ((rc = ensure(ctx, d.d_misc, 4 * sizeof(uint64_t), false))) return rc;
+    if ((rc = ensure(ctx, d.h_misc, 4 * sizeof(uint64_t), true))) return rc;
+    B2P_CUDA(ctx, cudaMemcpyAsync(d.d_states.ptr, states + sh.lo, nl * sizeof(b2p_state16), cudaMemcpyHostToDevice, d.stream));
+    B2P_CUDA(ctx, cudaMemsetAsync(d.d_misc.ptr, 0, 4 * sizeof(uint64_t), d.stream));
+    B2P_CUDA(ctx, cudaMemsetAsync(d.d_plies.ptr, 0, nl * 2 * sizeof(uint32_t), d.stream));
+    PlayoutParams prm;
+    std::memset(&prm, 0, sizeof prm);
+    prm.states = reinterpret_cast<const uint4 *>(d.d_states.ptr);
+    prm.n = (uint32_t)nl;
+    prm.total = (uint32_t)tl;
+    prm.rep_stride = n;
+    prm.key = key;
+    prm.pid_base = pid_base + sh.lo;
+    prm.max_plies = -1;
+    prm.leaf_wins = (unsigned int *)d.d_plies.ptr;
+    prm.counters = (unsigned long long *)d.d_misc.ptr;
+    prm.next = next_slot(d);
+    cudaError_t e = use_warp_kernel(sched, prm.total, km) ? launch_playout_warp(prm, km, d.sm_count, d.stream, nullptr)
+                                                      : launch_playout_lanes(prm, km, d.sm_count, d.stream, nullptr);
+    if (e != cudaSuccess) return fail(ctx, B2P_ECUDA, std::string("playout launch: ") + cudaGetErrorString(e));
+    ctx->launches++;
+    B2P_CUDA(ctx, cudaMemcpyAsync(wins_out + 2 * sh.lo, d.d_plies.ptr, nl * 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, d.stream));
+    B2P_CUDA(ctx, cudaMemcpyAsync(d.h_misc.ptr, d.d_misc.ptr, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, d.stream));
+  }
   for (int g = 0; g < G; g++) {
     Device &d = ctx->devs[g];
     B2P_CUDA(ctx, cudaSetDevice(d.id));

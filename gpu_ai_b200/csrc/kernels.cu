@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(kLaneBlock) playout_lanes_kernel(const Playout
   Game g;
   g.pos.own = g.pos.opp = g.pos.kings = 0;
   g.turn = g.msc = 0;
-  uint32_t w = 0, ply = 0, blk = 0;
+  uint32_t w = 0, ply = 0, blk = 0, my_leaf = 0;
   uint64_t pid = 0;
   int limit = prm.max_plies;
   bool busy = false;
@@ -93,6 +93,7 @@ __global__ void __launch_bounds__(kLaneBlock) playout_lanes_kernel(const Playout
             leaf = w - rep * prm.n;
           }
           pid = prm.pid_base + (uint64_t)rep * prm.rep_stride + leaf;
+          if (LIMITED) my_leaf = leaf;
           if (kLeaf) {
             g = load_game(0x00000FFFu, 0xFFF00000u, 0u, 0u);  // getStartingState, src/state.cpp:25-40
           } else {
@@ -147,6 +148,7 @@ __global__ void __launch_bounds__(kLaneBlock) playout_lanes_kernel(const Playout
           store_game(g, o);
           prm.final_states[w] = make_uint4(o[0], o[1], o[2], o[3]);
         }
+        if (prm.leaf_wins && (res == 0 || res == 1)) atomicAdd(prm.leaf_wins + 2 * my_leaf + res, 1u);
       }
       c_none += res == -1;
       c_p1 += res == 0;
@@ -216,7 +218,7 @@ cudaError_t launch_lanes_t(const PlayoutParams &prm, int sm_count, cudaStream_t 
 
 cudaError_t launch_playout_lanes(const PlayoutParams &prm, KernelMode mode, int sm_count, cudaStream_t stream,
                                  LaunchInfo *info) {
-  const bool limited = prm.max_plies >= 0 || prm.plies != nullptr || prm.final_states != nullptr;
+  const bool limited = prm.max_plies >= 0 || prm.plies != nullptr || prm.final_states != nullptr || prm.leaf_wins != nullptr;
   switch (mode) {
     case kRandomCanonical:
       return limited ? launch_lanes_t<kRandomCanonical, true>(prm, sm_count, stream, info)

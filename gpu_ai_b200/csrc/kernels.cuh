@@ -17,6 +17,7 @@ struct PlayoutParams {
   int8_t *winners;              // [total] or null
   uint32_t *plies;              // [total] or null
   uint4 *final_states;          // [total] or null
+  unsigned int *leaf_wins;      // [n][2] PLAYER_1 / PLAYER_2 wins per leaf over all reps (atomically accumulated) or null
   unsigned long long *counters; // [4] draws, p1, p2, plies (atomically accumulated)
   unsigned int *next;           // work-queue head (zeroed by the launcher)
 };

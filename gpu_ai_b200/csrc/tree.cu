@@ -177,6 +177,24 @@ struct b2p_tree {
       }
   }
 
+  // update() for `reps` playouts per selected leaf given as win counts per leaf (b2p_run_counts)
+  void update_counts(int32_t id, const uint32_t *wins, uint32_t reps, uint32_t &pos, uint64_t &w1, uint64_t &w2) {
+    const uint32_t mine = nodes[id].assigned;
+    nodes[id].total += (uint64_t)mine * reps;
+    uint64_t a = 0, b = 0;
+    if (nodes[id].expanded) {
+      const uint32_t nc = nodes[id].n_children, fc = nodes[id].first_child;
+      for (uint32_t i = 0; i < nc; i++) update_counts((int32_t)(fc + i), wins, reps, pos, a, b);
+    } else {
+      for (uint32_t t = pos; t < pos + mine; t++) { a += wins[2 * t]; b += wins[2 * t + 1]; }
+      pos += mine;
+    }
+    nodes[id].wins[0] += a;
+    nodes[id].wins[1] += b;
+    w1 += a;
+    w2 += b;
+  }
+
   // GameTree::getScore (src/mcts.cpp:27-37)
   double score(const Node &n, int player) const {
     if (game_over(n)) return ((int)((n.state.meta & 1u) ^ 1u) == player) ? 1 : 0;
@@ -214,6 +232,18 @@ int b2p_tree_update(b2p_tree *t, const int8_t *winners, uint32_t n, uint32_t rep
   }
   uint32_t pos = 0;
   t->update(t->root, winners, n, reps, pos);
+  return B2P_OK;
+}
+
+int b2p_tree_update_counts(b2p_tree *t, const uint32_t *wins, uint32_t n, uint32_t reps) {
+  if (!t || (n && !wins) || reps == 0) return B2P_EINVAL;
+  if (t->nodes[t->root].assigned != n) {
+    t->err = "b2p_tree_update_counts: result count does not match the last select";
+    return B2P_EINVAL;
+  }
+  uint32_t pos = 0;
+  uint64_t a = 0, b = 0;
+  t->update_counts(t->root, wins, reps, pos, a, b);
   return B2P_OK;
 }
 
@@ -322,7 +352,7 @@ int b2p_tree_search(b2p_ctx *ctx, b2p_tree *t, uint32_t iterations, double secon
                     uint32_t reps, int mode, uint64_t key, uint64_t *playouts_out) {
   if (!ctx || !t || reps == 0 || initial_batch == 0) return B2P_EINVAL;
   std::vector<b2p_state16> leaves;
-  std::vector<int8_t> winners;
+  std::vector<uint32_t> wins;
   uint64_t played = 0;
   const double t0 = (double)clock() / CLOCKS_PER_SEC;
   struct timespec ts0;
@@ -340,17 +370,18 @@ int b2p_tree_search(b2p_ctx *ctx, b2p_tree *t, uint32_t iterations, double secon
     uint32_t n = (uint32_t)((double)(total / reps) * scale);
     if (n < initial_batch) n = initial_batch;
     leaves.resize(n);
-    winners.resize((size_t)n * reps);
+    wins.resize((size_t)n * 2);
     uint32_t got = 0;
     t->select(t->root, n, leaves.data(), got);
-    int rc = b2p_run_packed(ctx, leaves.data(), got, reps, key + it, played, mode, B2P_SCHED_AUTO, B2P_ORDER_FAST, -1,
-                            winners.data(), nullptr, nullptr, nullptr);
+    // 16 B per leaf up, 8 B per leaf down: the per-playout winners stay on the device
+    int rc = b2p_run_counts(ctx, leaves.data(), got, reps, key + it, played, mode, B2P_SCHED_AUTO, B2P_ORDER_FAST, wins.data(), nullptr);
     if (rc != B2P_OK) {
       t->err = std::string("b2p_tree_search: ") + b2p_last_error(ctx);
       return rc;
     }
     uint32_t pos = 0;
-    t->update(t->root, winners.data(), got, reps, pos);
+    uint64_t a = 0, b = 0;
+    t->update_counts(t->root, wins.data(), reps, pos, a, b);
     played += (uint64_t)got * reps;
   }
   if (playouts_out) *playouts_out = played;

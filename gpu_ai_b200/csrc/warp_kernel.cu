@@ -244,6 +244,7 @@ __global__ void __launch_bounds__(kWarpBlock) playout_warp_kernel(const PlayoutP
         store_game(g, o);
         prm.final_states[w] = make_uint4(o[0], o[1], o[2], o[3]);
       }
+      if (prm.leaf_wins && (res == 0 || res == 1)) atomicAdd(prm.leaf_wins + 2 * leaf + res, 1u);
       c_none += res == -1;
       c_p1 += res == 0;
       c_p2 += res == 1;

@@ -40,6 +40,7 @@ ABI = [
     ("b2p_version", C.c_char_p, []),
     ("b2p_run_states776", _INT, [_VP, _VP, _SZ, _INT, _INT, _VP]),
     ("b2p_run_packed", _INT, [_VP, _VP, _SZ, _U32, _U64, _U64, _INT, _INT, _INT, _INT, _VP, _VP, _VP, _VP]),
+    ("b2p_run_counts", _INT, [_VP, _VP, _SZ, _U32, _U64, _U64, _INT, _INT, _INT, _VP, _VP]),
     ("b2p_genmoves", _INT, [_VP, _VP, _SZ, _INT, _VP, _VP]),
     ("b2p_run_packed_device", _INT, [_VP, _INT, _VP, _SZ, _U32, _U64, _U64, _INT, _INT, _INT, _INT, _VP, _VP, _VP, _VP, _VP]),
     ("b2p_genmoves_device", _INT, [_VP, _INT, _VP, _SZ, _INT, _VP, _VP, _VP]),
@@ -55,6 +56,7 @@ ABI = [
     ("b2p_tree_destroy", None, [_VP]),
     ("b2p_tree_select", _INT, [_VP, _U32, _VP, C.POINTER(_U32)]),
     ("b2p_tree_update", _INT, [_VP, _VP, _U32, _U32]),
+    ("b2p_tree_update_counts", _INT, [_VP, _VP, _U32, _U32]),
     ("b2p_tree_best_move", _INT, [_VP, _INT, C.POINTER(_U64)]),
     ("b2p_tree_move", _INT, [_VP, _U64]),
     ("b2p_tree_info", _INT, [_VP, _VP]),
@@ -170,6 +172,15 @@ class Engine:
                                             _ptr(winners), _ptr(plies), _ptr(final), _ptr(counters)))
         return winners, plies, final, counters
 
+    def run_counts(self, states, reps, key=12345, pid_base=0, mode=MODE_RANDOM, sched=SCHED_THREAD, order=ORDER_FAST):
+        """`reps` playouts per leaf; returns (wins[n, 2] uint32, counters[4])."""
+        a = _as_packed(states)
+        n = a.shape[0]
+        wins = np.zeros((n, 2), dtype=np.uint32)
+        counters = np.zeros(4, dtype=np.uint64)
+        self._check(self.lib.b2p_run_counts(self.ctx, _ptr(a), n, reps, key, pid_base, mode, sched, order, _ptr(wins), _ptr(counters)))
+        return wins, counters
+
     def genmoves(self, states, max_moves=64):
         a = _as_packed(states)
         n = a.shape[0]
@@ -237,6 +248,10 @@ class Tree:
     def update(self, winners, reps=1):
         w = np.ascontiguousarray(winners, dtype=np.int8)
         self._check(self.lib.b2p_tree_update(self.h, _ptr(w), w.size // reps, reps))
+
+    def update_counts(self, wins, reps):
+        w = np.ascontiguousarray(wins, dtype=np.uint32)
+        self._check(self.lib.b2p_tree_update_counts(self.h, _ptr(w), w.size // 2, reps))
 
     def best_move(self, player):
         m = _U64()

@@ -105,6 +105,12 @@ int b2p_run_packed(b2p_ctx *ctx, const b2p_state16 *states, size_t n, uint32_t r
                    int mode, int sched, int order, int max_plies, int8_t *winners_out, uint32_t *plies_out,
                    b2p_state16 *final_out, uint64_t counters_out[4]);
 
+/* K playouts per leaf with win COUNTS per leaf returned: wins_out[2*i + p] = number of the
+ * `reps` playouts from states[i] won by PLAYER_(p+1); draws = reps - both.  Same playout ids and rules as
+ * b2p_run_packed; only 8 bytes per leaf come back. */
+int b2p_run_counts(b2p_ctx *ctx, const b2p_state16 *states, size_t n, uint32_t reps, uint64_t key, uint64_t pid_base,
+                   int mode, int sched, int order, uint32_t *wins_out, uint64_t counters_out[4]);
+
 /* ---- move generation (replaces genMovesKernel / genMovesTest, src/genMovesTest.cu:10-100) ----
  * moves_out[i*max_moves + k] = k-th move of State::getMoves() for states[i] (k < max_moves);
  * counts_out[i] = number of legal moves (may exceed max_moves). */
@@ -165,6 +171,8 @@ int b2p_tree_select(b2p_tree *tree, uint32_t trials, b2p_state16 *leaves_out, ui
 /* GameTree::update (src/mcts.cpp:159-180).  winners: PlayerId per trial of the last select, n = its leaf count;
  * reps > 1: `reps` playouts per selected leaf laid out [rep][leaf] exactly as b2p_run_packed returns them */
 int b2p_tree_update(b2p_tree *tree, const int8_t *winners, uint32_t n, uint32_t reps);
+/* the same with per-leaf win counts (b2p_run_counts layout): every selected leaf was played `reps` times */
+int b2p_tree_update_counts(b2p_tree *tree, const uint32_t *wins, uint32_t n, uint32_t reps);
 int b2p_tree_best_move(const b2p_tree *tree, int player, b2p_move_t *move_out);   /* GameTree::getOptMove */
 int b2p_tree_move(b2p_tree *tree, b2p_move_t move);                      /* GameTree::move (subtree reuse) */
 int b2p_tree_info(const b2p_tree *tree, b2p_tree_stats *out);

@@ -295,3 +295,14 @@ def test_tree_search_on_gpu(engine, port):
     # subtree reuse keeps the statistics of the chosen child
     t.move(best)
     assert t.info()["total_trials"] == int(tr[list(mv).index(best)])
+
+
+def test_run_counts_equals_winner_tally(engine):
+    import gpu_ai_b200 as b
+    st = engine.gen_leaves(30000, key=4)
+    for sched, n in ((b.SCHED_THREAD, 30000), (b.SCHED_WARP, 3000)):
+        w, _, _, c = engine.run_packed(st[:n], reps=6, key=8, pid_base=77, order=ORDER_FAST, sched=sched)
+        wins, c2 = engine.run_counts(st[:n], reps=6, key=8, pid_base=77, order=ORDER_FAST, sched=sched)
+        w = w.reshape(6, n)
+        assert np.array_equal(wins[:, 0], (w == 0).sum(axis=0)) and np.array_equal(wins[:, 1], (w == 1).sum(axis=0))
+        assert np.array_equal(c, c2)

@@ -113,3 +113,18 @@ def test_tree_reps_and_errors():
     assert len(mv) == 7 and tr.sum() == 200
     with pytest.raises(b.B2PError):
         t.move(0xFFFF)                                   # not a legal root move
+
+
+def test_update_counts_equals_update_with_winners():
+    import gpu_ai_b200 as b
+    a, c = b.Tree(START_PACKED), b.Tree(START_PACKED)
+    reps = 5
+    for it, n in enumerate([50, 300, 7, 1000]):
+        la, lc = a.select(n), c.select(n)
+        assert np.array_equal(la, lc)
+        w = np.stack([fake_winners(la, 100 * it + r) for r in range(reps)])       # [rep][leaf]
+        a.update(w.reshape(-1), reps=reps)
+        c.update_counts(np.stack([(w == 0).sum(axis=0), (w == 1).sum(axis=0)], axis=1), reps)
+        assert a.info()["total_trials"] == c.info()["total_trials"] and a.info()["wins"] == c.info()["wins"]
+        for x, y in zip(a.root_moves(), c.root_moves()):
+            assert np.array_equal(x, y)
