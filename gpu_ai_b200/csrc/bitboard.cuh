@@ -34,8 +34,10 @@
 // only uses its result conditionally
 #if defined(__CUDA_ARCH__)
 #define B2P_PIN_FLOAT(x) asm volatile("" : "+f"(x))
+#define B2P_PIN_INT(x) asm volatile("" : "+r"(x))
 #else
 #define B2P_PIN_FLOAT(x) ((void)(x))
+#define B2P_PIN_INT(x) ((void)(x))
 #endif
 
 namespace b2p {

@@ -246,6 +246,42 @@ B2P_HD void finish_ply(Game &g, bool capture, uint32_t from, uint32_t to, uint32
   g.turn ^= 1u;
 }
 
+// Shape of a capture ply:
+//   0  every capture is a single hop: one list entry per (origin, first direction);
+//   1  some man hops on, but no landing square offers a choice and no king can hop twice: still
+//      exactly one sequence per first hop, in first-hop order -- pick the first hop on the common
+//      branch-free path, then follow the forced chain (a few instructions);
+//   2  a landing square offers a choice, or a king can hop twice: full enumeration.
+// A man makes at most 3 hops, so choices can only arise on the first two landing squares.
+B2P_HD int capture_shape(const Pos &p, const JumpMasks &jm, const uint32_t cap[4]) {
+  const uint32_t K = p.kings, men = ~K;
+  const uint32_t up = jm.j[0] | jm.j[1];
+  const uint32_t land_king = jumpUR(cap[0] & K) | jumpUL(cap[1] & K) | jumpDR(cap[2]) | jumpDL(cap[3]);
+  if (land_king & (up | jm.j[2] | jm.j[3])) return 2;
+  const uint32_t l1 = jumpUR(cap[0] & men) | jumpUL(cap[1] & men);
+  if ((l1 & up) == 0) return 0;
+  const uint32_t l2 = jumpUR(l1 & jm.j[0]) | jumpUL(l1 & jm.j[1]);
+  return ((jm.j[0] & jm.j[1]) & (l1 | l2)) ? 2 : 1;
+}
+
+// shapes 0 and 1: the move list has one entry per first hop (or step).  Returns the number of legal moves.
+template <int ORDER>
+B2P_HD int pick_first_hop_and_chain(const Pos &p, const PlyMasks &m, int shape, uint32_t turn, uint32_t r, uint32_t &from,
+                                    uint32_t &to, uint32_t &captured) {
+  const int n = pick_single_hop<ORDER>(p, m, turn, r, from, to, captured);
+  if (n != 0 && shape == 1 && !(p.kings & from)) {
+    // forced continuation of a man's capture: at most two more hops, never a choice
+    int cur = lowbit(to);
+    while (((m.jm.j[0] | m.jm.j[1]) >> cur) & 1u) {
+      const int d = (int)((m.jm.j[1] >> cur) & 1u);  // 1 = UL, 0 = UR (exactly one is available)
+      captured |= 1u << step_target(cur, d);
+      cur = jump_target(cur, d);
+    }
+    to = 1u << cur;
+  }
+  return n;
+}
+
 // One ply with a uniformly random legal move chosen by the 32-bit draw r:
 // rank j = mulhi32(r, n) in the list order ORDER (bitboard.cuh).  Returns kRunning, or the
 // winner when the game is over BEFORE a move is made: -1 if msc >= 50 (the draw test wins
@@ -256,10 +292,11 @@ B2P_HD int random_ply(Game &g, uint32_t r) {
   const Pos p = g.pos;
   const PlyMasks m = ply_masks(p);
   uint32_t from, to, captured;
-  if (m.capture && any_second_hop(p, m.jm, m.cap)) {
+  const int shape = m.capture ? capture_shape(p, m.jm, m.cap) : 0;
+  if (shape == 2) {
     pick_multi_hop_capture(p, m.jm, m.cap, r, ORDER == kOrderCanonical && g.turn != 0, from, to, captured);
   } else {
-    if (pick_single_hop<ORDER>(p, m, g.turn, r, from, to, captured) == 0) return (int)(g.turn ^ 1u);
+    if (pick_first_hop_and_chain<ORDER>(p, m, shape, g.turn, r, from, to, captured) == 0) return (int)(g.turn ^ 1u);
   }
   finish_ply(g, m.capture, from, to, captured);
   return kRunning;
@@ -404,14 +441,18 @@ B2P_HD int heuristic_ply(Game &g, NoiseBlock &&noise_block, Gauss &&gauss) {
         }
       }
     }
+    // one shared tail for the capture and the direct case (the flag is made opaque so that the
+    // compiler does not clone the 90-instruction index -> move mapping per case)
+    int is_capture = m.capture ? 1 : 0;
+    B2P_PIN_INT(is_capture);
     const int sel = select_origin_major(a, rev ? n - 1 - best.idx : best.idx);
     const int o = sel & 31;
     int d = sel >> 5;
-    if (m.capture && ((ownMen >> o) & 1u)) d ^= 1;
+    if (is_capture && ((ownMen >> o) & 1u)) d ^= 1;
     const int mid = step_target(o, d);
     from = 1u << o;
-    to = 1u << (m.capture ? jump_target(o, d) : mid);
-    captured = m.capture ? (1u << mid) : 0u;
+    to = 1u << (is_capture ? jump_target(o, d) : mid);
+    captured = is_capture ? (1u << mid) : 0u;
   }
   finish_ply(g, m.capture, from, to, captured);
   return kRunning;

@@ -69,7 +69,8 @@ __device__ __forceinline__ int warp_random_ply(Game &g, uint32_t r, unsigned lan
   const Pos p = g.pos;
   const PlyMasks m = ply_masks(p);
   uint32_t from = 0, to = 0, captured = 0;
-  if (m.capture && any_second_hop(p, m.jm, m.cap)) {
+  const int shape = m.capture ? capture_shape(p, m.jm, m.cap) : 0;
+  if (shape == 2) {
     // lane = origin square: every capturing piece enumerates its own sequences in parallel
     const uint32_t origins = m.cap[0] | m.cap[1] | m.cap[2] | m.cap[3];
     const bool mine = (origins >> lane) & 1u;
@@ -94,8 +95,8 @@ __device__ __forceinline__ int warp_random_ply(Game &g, uint32_t r, unsigned lan
     to = __shfl_sync(kFull, to, src);
     captured = __shfl_sync(kFull, captured, src);
   } else {
-    // single-hop lists: the bitboard word is already the 32-lane vector; uniform across the warp
-    if (pick_single_hop<ORDER>(p, m, g.turn, r, from, to, captured) == 0) return (int)(g.turn ^ 1u);
+    // one entry per first hop: the bitboard word is already the 32-lane vector; uniform across the warp
+    if (pick_first_hop_and_chain<ORDER>(p, m, shape, g.turn, r, from, to, captured) == 0) return (int)(g.turn ^ 1u);
   }
   finish_ply(g, m.capture, from, to, captured);
   return kRunning;

@@ -306,19 +306,29 @@ uint64_t or_encode_move(const or_move *m) {
 
 /* ------------------------------------------------------------------ */
 /* fast-order rank: the order in which the throughput kernel enumerates  */
-/* the legal moves (DESIGN.md "move order").  Positions that contain a   */
-/* multi-hop capture keep the canonical order.  Otherwise moves are       */
-/* sorted by (slot, origin as seen by the mover): slot = position of the  */
-/* move among the reference's per-square generator order, origin in the   */
-/* mover's frame = square index for P1, 31 - index for P2.                */
+/* the legal moves (DESIGN.md "move order").  Positions whose capture     */
+/* list needs a full enumeration (see below) keep the canonical order.    */
+/* Otherwise moves are sorted by (direction of the first hop or step as   */
+/* seen by the mover, origin in the mover's frame = square index for P1,  */
+/* 31 - index for P2).                                                    */
 /* Returns the canonical index of the move with fast-order rank j.        */
 /* ------------------------------------------------------------------ */
 static int fast_order_pick(const or_state *s, const or_move *mv, int n, int j) {
-  for (int i = 0; i < n; i++)
-    if (mv[i].hops >= 2) return s->turn == OR_P1 ? j : n - 1 - j;
+  /* full enumeration shape: a king sequence with >= 2 hops, or two sequences that share origin and first
+   * landing square (a choice on a later square) -> canonical order (reversed for PLAYER_2) */
+  int full = 0;
+  for (int i = 0; i < n && !full; i++) {
+    if (mv[i].hops >= 2 && s->at[mv[i].fr][mv[i].fc].king) full = 1;
+    for (int k = i + 1; k < n && !full; k++)
+      if (mv[i].hops >= 1 && mv[k].hops >= 1 && mv[i].fr == mv[k].fr && mv[i].fc == mv[k].fc &&
+          mv[i].via_r[0] == mv[k].via_r[0] && mv[i].via_c[0] == mv[k].via_c[0]) full = 1;
+  }
+  if (full) return s->turn == OR_P1 ? j : n - 1 - j;
   int key[OR_MAX_MOVES];
   for (int i = 0; i < n; i++) {
-    int dr = (mv[i].tr > mv[i].fr) ? 1 : -1, dc = (mv[i].tc > mv[i].fc) ? 1 : -1;
+    /* direction of the first hop (or of the step) */
+    int t_r = mv[i].hops ? mv[i].via_r[0] : mv[i].tr, t_c = mv[i].hops ? mv[i].via_c[0] : mv[i].tc;
+    int dr = (t_r > mv[i].fr) ? 1 : -1, dc = (t_c > mv[i].fc) ? 1 : -1;
     /* direction as seen by the mover (board rotated by 180 degrees for P2) */
     if (s->turn == OR_P2) { dr = -dr; dc = -dc; }
     int dir = dr > 0 ? (dc > 0 ? 0 : 1) : (dc > 0 ? 2 : 3); /* UR, UL, DR, DL */

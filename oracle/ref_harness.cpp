@@ -85,11 +85,17 @@ uint64_t encode(const Move &m) {
 
 // same definition as fast_order_pick() in checkers_oracle.c, on reference types
 int fast_order_pick(const State &s, const Move *mv, int n, int j) {
-  for (int i = 0; i < n; i++)
-    if (mv[i].jumps >= 2) return s.turn == PLAYER_1 ? j : n - 1 - j;
+  bool full = false;
+  for (int i = 0; i < n && !full; i++) {
+    if (mv[i].jumps >= 2 && s[mv[i].from].type == CHECKER_KING) full = true;
+    for (int k = i + 1; k < n && !full; k++)
+      if (mv[i].jumps >= 1 && mv[k].jumps >= 1 && mv[i].from == mv[k].from && mv[i].intermediate[0] == mv[k].intermediate[0]) full = true;
+  }
+  if (full) return s.turn == PLAYER_1 ? j : n - 1 - j;
   std::vector<int> key(n);
   for (int i = 0; i < n; i++) {
-    int dr = mv[i].to.row > mv[i].from.row ? 1 : -1, dc = mv[i].to.col > mv[i].from.col ? 1 : -1;
+    const Loc first = mv[i].jumps ? mv[i].intermediate[0] : mv[i].to;  // first hop (or the step)
+    int dr = first.row > mv[i].from.row ? 1 : -1, dc = first.col > mv[i].from.col ? 1 : -1;
     if (s.turn == PLAYER_2) { dr = -dr; dc = -dc; }
     int dir = dr > 0 ? (dc > 0 ? 0 : 1) : (dc > 0 ? 2 : 3);
     int origin = (int)loc_square(mv[i].from);
