@@ -97,19 +97,24 @@ class ClockSampler:
 
     def _poll(self):
         nv, h = self.nvml
+        try:
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        except Exception:
+            mx = 0
+        reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        k = 0
+        pw = 0.0
         while not self.stop_flag.is_set():
             try:
                 sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
-                mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
-                try:
-                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
-                except Exception:
-                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                rs = reasons(h)
+                if k % 4 == 0:
+                    pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
                 self.samples.append((sm, mx, pw, rs))
+                k += 1
             except Exception:
                 pass
-            time.sleep(0.01)
+            time.sleep(0.005)
 
     def _read(self):
         for line in self.proc.stdout:
