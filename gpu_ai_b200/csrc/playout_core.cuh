@@ -248,20 +248,34 @@ B2P_HD void finish_ply(Game &g, bool capture, uint32_t from, uint32_t to, uint32
 
 // Shape of a capture ply:
 //   0  every capture is a single hop: one list entry per (origin, first direction);
-//   1  some man hops on, but no landing square offers a choice and no king can hop twice: still
-//      exactly one sequence per first hop, in first-hop order -- pick the first hop on the common
-//      branch-free path, then follow the forced chain (a few instructions);
-//   2  a landing square offers a choice, or a king can hop twice: full enumeration.
-// A man makes at most 3 hops, so choices can only arise on the first two landing squares.
+//   1  some piece hops on, but never with a choice: men along forced chains (<= 3 hops), kings with at
+//      most one forced second hop.  Still exactly one sequence per first hop, in first-hop order -- pick
+//      the first hop on the common branch-free path, then follow the forced chain (a few instructions);
+//   2  a landing square offers a choice, or a king could hop a third time: full enumeration.
+// A man makes at most 3 hops, so its choices can only arise on the first two landing squares.  For a king
+// the hop back over the piece it just jumped is never available on its FIRST landing square (its origin
+// is still occupied on the unmodified board) and is explicitly excluded on the second.
 B2P_HD int capture_shape(const Pos &p, const JumpMasks &jm, const uint32_t cap[4]) {
   const uint32_t K = p.kings, men = ~K;
-  const uint32_t up = jm.j[0] | jm.j[1];
+  const uint32_t up = jm.j[0] | jm.j[1], down = jm.j[2] | jm.j[3];
+  uint32_t full = 0, multi = 0;  // single exit, bitwise accumulation: keeps the warp on one path
   const uint32_t land_king = jumpUR(cap[0] & K) | jumpUL(cap[1] & K) | jumpDR(cap[2]) | jumpDL(cap[3]);
-  if (land_king & (up | jm.j[2] | jm.j[3])) return 2;
+  if (land_king & (up | down)) {
+    multi = 1;
+    // two or more onward hops from a first landing square?
+    full = land_king & ((jm.j[0] & jm.j[1]) | (jm.j[2] & jm.j[3]) | (up & down));
+    // a third hop from a second landing square (arrival direction d, so opp(d) = 3 - d is excluded)?
+    const uint32_t b0 = jumpUR(land_king & jm.j[0]), b1 = jumpUL(land_king & jm.j[1]);
+    const uint32_t b2 = jumpDR(land_king & jm.j[2]), b3 = jumpDL(land_king & jm.j[3]);
+    full |= (b0 & (up | jm.j[2])) | (b1 & (up | jm.j[3])) | (b2 & (down | jm.j[0])) | (b3 & (down | jm.j[1]));
+  }
   const uint32_t l1 = jumpUR(cap[0] & men) | jumpUL(cap[1] & men);
-  if ((l1 & up) == 0) return 0;
   const uint32_t l2 = jumpUR(l1 & jm.j[0]) | jumpUL(l1 & jm.j[1]);
-  return ((jm.j[0] & jm.j[1]) & (l1 | l2)) ? 2 : 1;
+  multi |= l1 & up;
+  full |= (jm.j[0] & jm.j[1]) & (l1 | l2);
+  int shape = full ? 2 : (multi ? 1 : 0);
+  B2P_PIN_INT(shape);  // opaque: the callers' common path must not be cloned per shape
+  return shape;
 }
 
 // shapes 0 and 1: the move list has one entry per first hop (or step).  Returns the number of legal moves.
@@ -269,13 +283,24 @@ template <int ORDER>
 B2P_HD int pick_first_hop_and_chain(const Pos &p, const PlyMasks &m, int shape, uint32_t turn, uint32_t r, uint32_t &from,
                                     uint32_t &to, uint32_t &captured) {
   const int n = pick_single_hop<ORDER>(p, m, turn, r, from, to, captured);
-  if (n != 0 && shape == 1 && !(p.kings & from)) {
-    // forced continuation of a man's capture: at most two more hops, never a choice
+  if (n != 0 && shape == 1) {
     int cur = lowbit(to);
-    while (((m.jm.j[0] | m.jm.j[1]) >> cur) & 1u) {
-      const int d = (int)((m.jm.j[1] >> cur) & 1u);  // 1 = UL, 0 = UR (exactly one is available)
-      captured |= 1u << step_target(cur, d);
-      cur = jump_target(cur, d);
+    if (p.kings & from) {
+      // king: at most one forced second hop (shape 1 guarantees there is no third)
+      const uint32_t nib = ((m.jm.j[0] >> cur) & 1u) | (((m.jm.j[1] >> cur) & 1u) << 1) | (((m.jm.j[2] >> cur) & 1u) << 2) |
+                           (((m.jm.j[3] >> cur) & 1u) << 3);
+      if (nib) {
+        const int d = lowbit(nib);
+        captured |= 1u << step_target(cur, d);
+        cur = jump_target(cur, d);
+      }
+    } else {
+      // man: forced continuation, at most two more hops, never a choice
+      while (((m.jm.j[0] | m.jm.j[1]) >> cur) & 1u) {
+        const int d = (int)((m.jm.j[1] >> cur) & 1u);  // 1 = UL, 0 = UR (exactly one is available)
+        captured |= 1u << step_target(cur, d);
+        cur = jump_target(cur, d);
+      }
     }
     to = 1u << cur;
   }
@@ -292,7 +317,9 @@ B2P_HD int random_ply(Game &g, uint32_t r) {
   const Pos p = g.pos;
   const PlyMasks m = ply_masks(p);
   uint32_t from, to, captured;
-  const int shape = m.capture ? capture_shape(p, m.jm, m.cap) : 0;
+  // evaluated by every lane (all-zero masks when there is no capture): a lane-dependent branch around it
+  // would split the warp before the common selection path and run that path twice
+  const int shape = capture_shape(p, m.jm, m.cap);
   if (shape == 2) {
     pick_multi_hop_capture(p, m.jm, m.cap, r, ORDER == kOrderCanonical && g.turn != 0, from, to, captured);
   } else {

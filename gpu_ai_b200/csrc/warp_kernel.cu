@@ -69,7 +69,7 @@ __device__ __forceinline__ int warp_random_ply(Game &g, uint32_t r, unsigned lan
   const Pos p = g.pos;
   const PlyMasks m = ply_masks(p);
   uint32_t from = 0, to = 0, captured = 0;
-  const int shape = m.capture ? capture_shape(p, m.jm, m.cap) : 0;
+  const int shape = capture_shape(p, m.jm, m.cap);
   if (shape == 2) {
     // lane = origin square: every capturing piece enumerates its own sequences in parallel
     const uint32_t origins = m.cap[0] | m.cap[1] | m.cap[2] | m.cap[3];

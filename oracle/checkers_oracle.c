@@ -314,11 +314,11 @@ uint64_t or_encode_move(const or_move *m) {
 /* Returns the canonical index of the move with fast-order rank j.        */
 /* ------------------------------------------------------------------ */
 static int fast_order_pick(const or_state *s, const or_move *mv, int n, int j) {
-  /* full enumeration shape: a king sequence with >= 2 hops, or two sequences that share origin and first
+  /* full enumeration shape: a king sequence with >= 3 hops, or two sequences that share origin and first
    * landing square (a choice on a later square) -> canonical order (reversed for PLAYER_2) */
   int full = 0;
   for (int i = 0; i < n && !full; i++) {
-    if (mv[i].hops >= 2 && s->at[mv[i].fr][mv[i].fc].king) full = 1;
+    if (mv[i].hops >= 3 && s->at[mv[i].fr][mv[i].fc].king) full = 1;
     for (int k = i + 1; k < n && !full; k++)
       if (mv[i].hops >= 1 && mv[k].hops >= 1 && mv[i].fr == mv[k].fr && mv[i].fc == mv[k].fc &&
           mv[i].via_r[0] == mv[k].via_r[0] && mv[i].via_c[0] == mv[k].via_c[0]) full = 1;

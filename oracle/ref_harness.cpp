@@ -87,7 +87,7 @@ uint64_t encode(const Move &m) {
 int fast_order_pick(const State &s, const Move *mv, int n, int j) {
   bool full = false;
   for (int i = 0; i < n && !full; i++) {
-    if (mv[i].jumps >= 2 && s[mv[i].from].type == CHECKER_KING) full = true;
+    if (mv[i].jumps >= 3 && s[mv[i].from].type == CHECKER_KING) full = true;
     for (int k = i + 1; k < n && !full; k++)
       if (mv[i].jumps >= 1 && mv[k].jumps >= 1 && mv[i].from == mv[k].from && mv[i].intermediate[0] == mv[k].intermediate[0]) full = true;
   }
