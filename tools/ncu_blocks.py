@@ -13,7 +13,8 @@ hdr = rows[1]
 ia, ie, it = hdr.index("Source"), hdr.index("Instructions Executed"), hdr.index("Avg. Threads Executed")
 data = [(r[ia].strip(), int(r[ie]), float(r[it])) for r in rows[2:] if len(r) > it]
 tot = sum(d[1] for d in data)
-loop = max(d[1] for d in data if d[2] >= 31.5 and "WARPSYNC" in d[0]) if any("WARPSYNC" in d[0] for d in data) else 0
+cands = [d[1] for d in data if d[2] >= 31.5 and "WARPSYNC" in d[0]]
+loop = max(cands) if cands else 0
 print("kernel:", rows[0][1][:90])
 print("total warp instructions %d; ply-loop iterations %d; warp-instr per iteration %.0f; lane-weighted avg threads %.2f"
       % (tot, loop, tot / loop if loop else 0, sum(d[1] * d[2] for d in data) / tot))
