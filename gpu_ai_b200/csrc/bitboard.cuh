@@ -35,7 +35,11 @@
 #if defined(__CUDA_ARCH__)
 #define B2P_PIN_FLOAT(x) asm volatile("" : "+f"(x))
 #define B2P_PIN_INT(x) asm volatile("" : "+r"(x))
+// explicit reconvergence of a known group of lanes: without it ptxas may keep sub-groups that took
+// different rare paths apart and run the common code after them once per sub-group
+#define B2P_REJOIN(mask) __syncwarp(mask)
 #else
+#define B2P_REJOIN(mask) ((void)(mask))
 #define B2P_PIN_FLOAT(x) ((void)(x))
 #define B2P_PIN_INT(x) ((void)(x))
 #endif
@@ -251,7 +255,7 @@ B2P_HD int select_origin_major(const uint32_t a[4], int k) {
   if (r >= 1) t &= t - 1;
   if (r >= 2) t &= t - 1;
   if (r >= 3) t &= t - 1;
-  return lo | (lowbit(t) << 5);
+  return lo | (lowbit(t | 16u) << 5);  // | 16: defined result (slot 4) when the masks are empty
 }
 
 // ---- capture sequences: iterative DFS over the static jump graph -----------------------------

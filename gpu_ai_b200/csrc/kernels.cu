@@ -116,6 +116,9 @@ __global__ void __launch_bounds__(kLaneBlock) playout_lanes_kernel(const Playout
 
 #pragma unroll 1
     for (int q = 0; q < 4; q++) {
+      // lanes that will play a heuristic ply in this slot (all 32 lanes are together at the loop top)
+      unsigned heur_lanes = 0;
+      if (kHeur) heur_lanes = __ballot_sync(kFull, busy && !((LIMITED || kLeaf) && limit >= 0 && (int)ply >= limit));
       if (!busy) continue;
       int res = kRunning;
       if (kLeaf && blk == 1 && q == 0) {
@@ -129,7 +132,7 @@ __global__ void __launch_bounds__(kLaneBlock) playout_lanes_kernel(const Playout
         res = random_ply<kOrderFast>(probe, 0u);
         if (res == kRunning) res = 3;  // marker: unfinished
       } else if (kHeur) {
-        res = heuristic_ply(g, [&](int b) { return philox_block(prm.key, pid, kDomainNoise | ((uint32_t)b << 8), ply); },
+        res = heuristic_ply(g, heur_lanes, [&](int b) { return philox_block(prm.key, pid, kDomainNoise | ((uint32_t)b << 8), ply); },
                             [&](uint32_t r) { return gauss_lookup(s_gauss, r); });
       } else {
         res = random_ply<kOrder>(g, pick4(rnd, q));

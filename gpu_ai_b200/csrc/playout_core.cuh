@@ -351,39 +351,71 @@ struct HeurBest {
 
 B2P_HD bool heur_better(float w, int idx, const HeurBest &b) { return w > b.w || (w == b.w && idx < b.idx); }
 
+// Staged for SIMT: every lane of the calling group walks through the same four stages, and the group is
+// explicitly rejoined (B2P_REJOIN) before the two expensive converged stages.  Without the rejoin points
+// ptxas keeps lanes that took different rare paths apart and runs the noise scan and the index -> move
+// mapping once per sub-group (measured: 1.8 executions per ply).  `lanes` = mask of the lanes that call this
+// function together (device; ignored on the host).  No early return before the last rejoin point.
 template <class NoiseBlock, class Gauss>
-B2P_HD int heuristic_ply(Game &g, NoiseBlock &&noise_block, Gauss &&gauss) {
-  if (g.msc >= kDrawPlies) return -1;
+B2P_HD int heuristic_ply(Game &g, unsigned lanes, NoiseBlock &&noise_block, Gauss &&gauss) {
+  (void)lanes;
   const Pos p = g.pos;
   const PlyMasks m = ply_masks(p);
+  const bool drawn = g.msc >= kDrawPlies;
   const uint32_t my = material(p.own, p.kings), his = material(p.opp, p.kings);
   const uint32_t ownMen = p.own & ~p.kings;
+  const uint32_t ownK = p.own & p.kings;
   const bool rev = g.turn != 0;  // canonical index = n-1-normalised index for PLAYER_2
+  const int shape = capture_shape(p, m.jm, m.cap);
+  // one list entry per (origin, slot): same four masks as the random path, canonical slot order
+  const uint32_t men = ~p.kings;
+  uint32_t a[4];
+  a[0] = m.capture ? ((m.cap[1] & men) | (m.cap[0] & p.kings)) : (p.own & m.e[0]);
+  a[1] = m.capture ? ((m.cap[0] & men) | (m.cap[1] & p.kings)) : (p.own & m.e[1]);
+  a[2] = m.capture ? m.cap[2] : (ownK & m.e[2]);
+  a[3] = m.capture ? m.cap[3] : (ownK & m.e[3]);
+  const int n = popc(a[0]) + popc(a[1]) + popc(a[2]) + popc(a[3]);
+  const bool enumerate = !drawn && shape != 0;        // some capture continues: sequences must be enumerated
+  const int n_scan = (drawn || enumerate) ? 0 : n;    // candidates handled by the converged scan
   uint32_t from = 0, to = 0, captured = 0;
   HeurBest best;
   best.w = -__builtin_inff();
   best.idx = 0x7fffffff;
-  int cached = -1;
-  Philox4 nb;
-  nb.v[0] = nb.v[1] = nb.v[2] = nb.v[3] = 0;
-  auto noise = [&](int idx) {
-    const int b = idx >> 3;
-    if (b != cached) { nb = noise_block(b); cached = b; }
-    const int q = (idx >> 1) & 3;
-    uint32_t r = nb.v[0];
-    r = q == 1 ? nb.v[1] : r;
-    r = q == 2 ? nb.v[2] : r;
-    r = q == 3 ? nb.v[3] : r;
-    return gauss((idx & 1) ? r >> 16 : r & 0xFFFFu);
-  };
-  if (m.capture && any_second_hop(p, m.jm, m.cap)) {
-    // multi-hop sequences: one register-DFS pass buffers the sequences, then they are scored in
-    // list order (the canonical index of PLAYER_2 needs the total count first)
+
+  // Weight classes.  Direct moves: plain / crowning.  Single-hop captures: (man | king captured) x
+  // (plain | crowning).  All candidates of a class share one weight, so the scan only needs to know, per
+  // canonical index, which class a candidate is in: two 64-bit index masks.
+  const uint32_t lo_den = m.capture ? his - 1u : his;
+  const uint32_t hi_den = his >= 4u ? his - 4u : his;  // only used when a king can be captured (his >= 4 then)
+  float w0 = (float)my / (float)lo_den, w1 = (float)(my + 3u) / (float)lo_den;
+  float w2 = (float)my / (float)hi_den, w3 = (float)(my + 3u) / (float)hi_den;
+  B2P_PIN_FLOAT(w0);
+  B2P_PIN_FLOAT(w1);
+  B2P_PIN_FLOAT(w2);
+  B2P_PIN_FLOAT(w3);
+  uint64_t crown_idx = 0, kingcap_idx = 0;
+
+  // ---- stage 1 (divergent, short): the rare work --------------------------------------------------------
+  if (enumerate) {
+    // multi-hop sequences: one register-DFS pass buffers the sequences, then they are scored in list order
+    int cached = -1;
+    Philox4 nb;
+    nb.v[0] = nb.v[1] = nb.v[2] = nb.v[3] = 0;
+    auto noise = [&](int idx) {
+      const int blk = idx >> 3;
+      if (blk != cached) { nb = noise_block(blk); cached = blk; }
+      const int q = (idx >> 1) & 3;
+      uint32_t r = nb.v[0];
+      r = q == 1 ? nb.v[1] : r;
+      r = q == 2 ? nb.v[2] : r;
+      r = q == 3 ? nb.v[3] : r;
+      return gauss((idx & 1) ? r >> 16 : r & 0xFFFFu);
+    };
     constexpr int kLeafBuf = 12;
     uint32_t buf_captured[kLeafBuf];
     uint16_t buf_from_to[kLeafBuf];
     int seen = 0;
-    const int n = for_each_capture(p, m.jm, [&](const CaptureMove &cm) {
+    const int total = for_each_capture(p, m.jm, [&](const CaptureMove &cm) {
       if (seen < kLeafBuf) {
         buf_captured[seen] = cm.captured;
         buf_from_to[seen] = (uint16_t)(cm.from | (cm.to << 5));
@@ -392,14 +424,14 @@ B2P_HD int heuristic_ply(Game &g, NoiseBlock &&noise_block, Gauss &&gauss) {
       return false;
     });
     auto score = [&](int i, int f, int t, uint32_t cap) {
-      const int idx = rev ? n - 1 - i : i;
+      const int idx = rev ? total - 1 - i : i;
       const uint32_t promo = (((ownMen >> f) & 1u) && t >= 28) ? 3u : 0u;
       const uint32_t loss = (uint32_t)(popc(cap) + 3 * popc(cap & p.kings));
       const float w = (float)(my + promo) / (float)(his - loss) + noise(idx);
       if (heur_better(w, idx, best)) { best.w = w; best.idx = idx; from = 1u << f; to = 1u << t; captured = cap; }
     };
-    for (int i = 0; i < n && i < kLeafBuf; i++) score(i, buf_from_to[i] & 31, buf_from_to[i] >> 5, buf_captured[i]);
-    if (n > kLeafBuf) {
+    for (int i = 0; i < total && i < kLeafBuf; i++) score(i, buf_from_to[i] & 31, buf_from_to[i] >> 5, buf_captured[i]);
+    if (total > kLeafBuf) {
       int i = 0;
       for_each_capture(p, m.jm, [&](const CaptureMove &cm) {
         if (i >= kLeafBuf) score(i, cm.from, cm.to, cm.captured);
@@ -407,80 +439,68 @@ B2P_HD int heuristic_ply(Game &g, NoiseBlock &&noise_block, Gauss &&gauss) {
         return false;
       });
     }
-  } else {
-    // one list entry per (origin, slot): same four masks as the random path, canonical slot order
-    const uint32_t ownK = p.own & p.kings;
-    const uint32_t men = ~p.kings;
-    uint32_t a[4];
-    a[0] = m.capture ? ((m.cap[1] & men) | (m.cap[0] & p.kings)) : (p.own & m.e[0]);
-    a[1] = m.capture ? ((m.cap[0] & men) | (m.cap[1] & p.kings)) : (p.own & m.e[1]);
-    a[2] = m.capture ? m.cap[2] : (ownK & m.e[2]);
-    a[3] = m.capture ? m.cap[3] : (ownK & m.e[3]);
-    const int n = popc(a[0]) + popc(a[1]) + popc(a[2]) + popc(a[3]);
-    if (n == 0) return (int)(g.turn ^ 1u);
-    if (!m.capture) {
-      // direct moves: one base weight; the few crowning moves (men one step from the far row) are
-      // marked by their canonical index so that the scan below never has to identify a move
-      float base = (float)my / (float)his, crowned = (float)(my + 3u) / (float)his;
-      B2P_PIN_FLOAT(base);
-      B2P_PIN_FLOAT(crowned);
-      const uint32_t cr0 = a[0] & ownMen & 0x0F000000u, cr1 = a[1] & ownMen & 0x0F000000u;
-      uint64_t crown_idx = 0;
-      for (uint32_t cr = cr0 | cr1; cr; cr &= cr - 1) {
-        const int o = lowbit(cr);
-        const uint32_t below = (1u << o) - 1u;
-        const int first = popc(a[0] & below) + popc(a[1] & below) + popc(a[2] & below) + popc(a[3] & below);
-        if ((cr0 >> o) & 1u) crown_idx |= 1ull << (rev ? n - 1 - first : first);
-        const int second = first + (int)((a[0] >> o) & 1u);
-        if ((cr1 >> o) & 1u) crown_idx |= 1ull << (rev ? n - 1 - second : second);
-      }
-      for (int b = 0; 8 * b < n; b++) {
-        const Philox4 blk = noise_block(b);
+  } else if (n_scan > 0) {
+    // class masks: a short loop over the FEW exceptional origins (crowning men for direct moves, the
+    // capturing pieces for captures)
+    uint32_t special = m.capture ? (a[0] | a[1] | a[2] | a[3]) : ((a[0] | a[1]) & ownMen & 0x0F000000u);
+    for (; special; special &= special - 1) {
+      const int o = lowbit(special);
+      const uint32_t below = (1u << o) - 1u;
+      int i = popc(a[0] & below) + popc(a[1] & below) + popc(a[2] & below) + popc(a[3] & below);
+      const bool man = (ownMen >> o) & 1u;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-        for (int q = 0; q < 8; q++) {
-          const int idx = 8 * b + q;
-          const uint32_t h = (q & 1) ? blk.v[q >> 1] >> 16 : blk.v[q >> 1] & 0xFFFFu;
-          const float w = (((crown_idx >> idx) & 1ull) ? crowned : base) + gauss(h);
-          if (idx < n && w > best.w) { best.w = w; best.idx = idx; }
-        }
-      }
-    } else {
-      // single-hop captures: few candidates, each with its own weight; walk them origin by origin
-      int i = 0;
-      for (uint32_t origins = a[0] | a[1] | a[2] | a[3]; origins; origins &= origins - 1) {
-        const int o = lowbit(origins);
-        const bool man = (ownMen >> o) & 1u;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-        for (int slot = 0; slot < 4; slot++) {
-          if (!((a[slot] >> o) & 1u)) continue;
-          const int d = man ? (slot ^ 1) : slot;
-          const int mid = step_target(o, d);
-          const uint32_t promo = (man && jump_target(o, d) >= 28) ? 3u : 0u;
-          const uint32_t loss = ((p.kings >> mid) & 1u) ? 4u : 1u;
-          const int idx = rev ? n - 1 - i : i;
-          const float w = (float)(my + promo) / (float)(his - loss) + noise(idx);
-          if (heur_better(w, idx, best)) { best.w = w; best.idx = idx; }
-          i++;
-        }
+      for (int slot = 0; slot < 4; slot++) {
+        if (!((a[slot] >> o) & 1u)) continue;
+        const int d = (m.capture && man) ? (slot ^ 1) : slot;
+        const int mid = step_target(o, d);
+        const int land = m.capture ? jump_target(o, d) : mid;
+        const int idx = rev ? n - 1 - i : i;
+        if (man && land >= 28) crown_idx |= 1ull << idx;
+        if (m.capture && ((p.kings >> mid) & 1u)) kingcap_idx |= 1ull << idx;
+        i++;
       }
     }
-    // one shared tail for the capture and the direct case (the flag is made opaque so that the
-    // compiler does not clone the 90-instruction index -> move mapping per case)
-    int is_capture = m.capture ? 1 : 0;
-    B2P_PIN_INT(is_capture);
-    const int sel = select_origin_major(a, rev ? n - 1 - best.idx : best.idx);
+  }
+
+  // ---- stage 2 (converged): scan the noise stream, 8 candidates per Philox block ------------------------
+  B2P_REJOIN(lanes);
+  for (int b = 0; 8 * b < n_scan; b++) {
+    const Philox4 blk = noise_block(b);
+    const uint32_t crown8 = (uint32_t)(crown_idx >> (8 * b)) & 0xFFu, kc8 = (uint32_t)(kingcap_idx >> (8 * b)) & 0xFFu;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int q = 0; q < 8; q++) {
+      const int idx = 8 * b + q;
+      const uint32_t h = (q & 1) ? blk.v[q >> 1] >> 16 : blk.v[q >> 1] & 0xFFFFu;
+      const bool crown = (crown8 >> q) & 1u, kc = (kc8 >> q) & 1u;
+      const float base = kc ? (crown ? w3 : w2) : (crown ? w1 : w0);
+      const float w = base + gauss(h);
+      if (idx < n_scan && w > best.w) { best.w = w; best.idx = idx; }
+    }
+  }
+
+  // ---- stage 3 (converged): winning index -> move -------------------------------------------------------
+  B2P_REJOIN(lanes);
+  {
+    const int pick = n_scan > 0 ? (rev ? n - 1 - best.idx : best.idx) : 0;
+    const int sel = select_origin_major(a, pick);
     const int o = sel & 31;
     int d = sel >> 5;
-    if (is_capture && ((ownMen >> o) & 1u)) d ^= 1;
+    if (m.capture && ((ownMen >> o) & 1u)) d ^= 1;
     const int mid = step_target(o, d);
-    from = 1u << o;
-    to = 1u << (is_capture ? jump_target(o, d) : mid);
-    captured = is_capture ? (1u << mid) : 0u;
+    if (n_scan > 0) {
+      from = 1u << o;
+      to = 1u << ((m.capture ? jump_target(o, d) : mid) & 31);
+      captured = m.capture ? (1u << (mid & 31)) : 0u;
+    }
   }
+
+  // ---- stage 4: outcome ---------------------------------------------------------------------------------
+  if (drawn) return -1;
+  if (!enumerate && n == 0) return (int)(g.turn ^ 1u);
   finish_ply(g, m.capture, from, to, captured);
   return kRunning;
 }

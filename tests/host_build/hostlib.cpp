@@ -56,7 +56,7 @@ void hb_playouts_batch(const uint32_t *packed, size_t n, uint32_t reps, uint64_t
         break;
       }
       if (mode == 1) {
-        res = heuristic_ply(g, [&](int b) { return philox_block(key, pid, kDomainNoise | ((uint32_t)b << 8), ply); },
+        res = heuristic_ply(g, 0u, [&](int b) { return philox_block(key, pid, kDomainNoise | ((uint32_t)b << 8), ply); },
                             [](uint32_t r) { return gauss_sigma(r); });
       } else {
         Philox4 b = philox_block(key, pid, kDomainRandom, ply >> 2);
