@@ -356,6 +356,22 @@ def main():
             ms1.append(a.elapsed_time(bb))
         out["single_pass"] = {"playouts": n, "ms": float(np.median(ms1)), "playouts_per_s": n / (float(np.median(ms1)) * 1e-3)}
 
+    # ---- the same workload with the strictly canonical move order (rank j -> j-th move of State::getMoves()) ------
+    if rank == 0 and mode == b.MODE_RANDOM and order == b.ORDER_FAST:
+        a, bb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for i in range(2):
+            eng.run_packed_device(d_states.data_ptr(), n, reps=reps, key=7 + i, mode=mode, order=b.ORDER_CANONICAL,
+                                  d_winners=d_winners.data_ptr(), d_counters=d_counters.data_ptr(), stream=stream)
+        a.record()
+        for i in range(3):
+            eng.run_packed_device(d_states.data_ptr(), n, reps=reps, key=17 + i, mode=mode, order=b.ORDER_CANONICAL,
+                                  d_winners=d_winners.data_ptr(), d_counters=d_counters.data_ptr(), stream=stream)
+        bb.record()
+        torch.cuda.synchronize()
+        out["canonical_order"] = {"playouts_per_s_per_gpu": 3 * n * reps / (a.elapsed_time(bb) * 1e-3),
+                                  "note": "B2P_ORDER_CANONICAL on this rank's GPU; the headline uses B2P_ORDER_FAST (same uniform law, "
+                                          "both bit-exact against the oracle)"}
+
     # ---- e2e: the reference-facing call, host buffers in and out ------------------------------------------------
     if not args.no_e2e:
         from gpu_ai_b200 import engine as eng_mod

@@ -464,18 +464,24 @@ B2P_HD int heuristic_ply(Game &g, unsigned lanes, NoiseBlock &&noise_block, Gaus
     }
   }
 
-  // ---- stage 2 (converged): scan the noise stream, 8 candidates per Philox block ------------------------
+  // ---- stage 2 (converged): scan the noise stream (8 candidates per Philox block) ------------------------
   B2P_REJOIN(lanes);
-  for (int b = 0; 8 * b < n_scan; b++) {
-    const Philox4 blk = noise_block(b);
-    const uint32_t crown8 = (uint32_t)(crown_idx >> (8 * b)) & 0xFFu, kc8 = (uint32_t)(kingcap_idx >> (8 * b)) & 0xFFu;
+  // half a Philox block (4 candidates) per trip: a lane with 9 candidates costs 3 trips, not 2 x 8
+  Philox4 blk;
+  blk.v[0] = blk.v[1] = blk.v[2] = blk.v[3] = 0;
+  for (int hb = 0; 4 * hb < n_scan; hb++) {
+    const bool upper = hb & 1;
+    if (!upper) blk = noise_block(hb >> 1);
+    const uint32_t word_a = upper ? blk.v[2] : blk.v[0], word_b = upper ? blk.v[3] : blk.v[1];
+    const uint32_t crown4 = (uint32_t)(crown_idx >> (4 * hb)) & 0xFu, kc4 = (uint32_t)(kingcap_idx >> (4 * hb)) & 0xFu;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (int q = 0; q < 8; q++) {
-      const int idx = 8 * b + q;
-      const uint32_t h = (q & 1) ? blk.v[q >> 1] >> 16 : blk.v[q >> 1] & 0xFFFFu;
-      const bool crown = (crown8 >> q) & 1u, kc = (kc8 >> q) & 1u;
+    for (int q = 0; q < 4; q++) {
+      const int idx = 4 * hb + q;
+      const uint32_t word = (q & 2) ? word_b : word_a;
+      const uint32_t h = (q & 1) ? word >> 16 : word & 0xFFFFu;
+      const bool crown = (crown4 >> q) & 1u, kc = (kc4 >> q) & 1u;
       const float base = kc ? (crown ? w3 : w2) : (crown ? w1 : w0);
       const float w = base + gauss(h);
       if (idx < n_scan && w > best.w) { best.w = w; best.idx = idx; }

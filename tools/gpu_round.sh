@@ -27,3 +27,9 @@ echo "== ncu full capture: heuristic kernel"
 timeout 1500 ncu --set full --clock-control none --import-source on -k regex:playout_lanes -s 4 -c 1 -f -o $OUT/prof_lanes_heuristic \
   python bench.py --steps 1 --warmup 3 --mode heuristic --reps 8 --no-cpu-baseline --no-e2e > $OUT/prof_heur_run.log 2>&1
 ls -la $OUT
+echo "== scheduler comparison"; timeout 600 python tools/sched_compare.py > $OUT/sched_compare.jsonl 2>&1; tail -2 $OUT/sched_compare.jsonl
+echo "== tests.sh-protocol sweep"; timeout 600 python tools/sweep.py 1 > $OUT/sweep_1gpu.jsonl 2>&1; tail -1 $OUT/sweep_1gpu.jsonl
+echo "== MCTS search throughput"; timeout 300 python tools/mcts_bench.py > $OUT/mcts_search_throughput.jsonl 2>&1; tail -2 $OUT/mcts_search_throughput.jsonl
+echo "== MCTS match (8 games)"; timeout 900 python tools/mcts_match.py --games 8 > $OUT/mcts_match.jsonl 2>&1; tail -1 $OUT/mcts_match.jsonl
+echo "== drop-in run_ai"; (timeout 300 shim/_ref/run_ai_b200 -m playout_test -n 200000 -1 device_single -2 host; timeout 300 shim/_ref/run_ai_b200 -m gen_moves_test -n 20000) > $OUT/run_ai_b200.txt 2>&1; tail -3 $OUT/run_ai_b200.txt
+ls -la $OUT
