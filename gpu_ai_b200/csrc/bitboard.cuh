@@ -173,16 +173,6 @@ B2P_HD void step_origins(const Pos &p, uint32_t out[4]) {
   out[3] = ownK & stepUR(empty);
 }
 
-// true if some capture can be extended by a second hop (then the move list is not just
-// "one entry per first hop" and the DFS below is needed)
-B2P_HD bool any_second_hop(const Pos &p, const JumpMasks &m, const uint32_t cap[4]) {
-  const uint32_t men = ~p.kings;
-  const uint32_t land_men = jumpUR(cap[0] & men) | jumpUL(cap[1] & men);
-  const uint32_t land_king = jumpUR(cap[0] & p.kings) | jumpUL(cap[1] & p.kings) | jumpDR(cap[2]) | jumpDL(cap[3]);
-  const uint32_t up = m.j[0] | m.j[1];
-  return ((land_men & up) | (land_king & (up | m.j[2] | m.j[3]))) != 0;
-}
-
 // ---- applying a move ----------------------------------------------------------------------
 // reference: State::move, src/state.cu:57-92.  `from`/`to` are single-bit masks, `captured`
 // the set of jumped squares (empty for a direct move).  A man that ends on row 7 (bits 28-31
