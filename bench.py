@@ -48,6 +48,9 @@ def parse():
     ap.add_argument("--leaves", type=int, default=LEAVES_PER_GPU, help="leaves per GPU")
     ap.add_argument("--mode", default="random", choices=["random", "heuristic"])
     ap.add_argument("--order", default="fast", choices=["fast", "canonical"])
+    ap.add_argument("--leaf-set", default="ref", choices=["ref", "live", "start"],
+                    help="D_ref = genRandomStates recipe (default, 36 %% terminal); D_live = D_ref without terminal leaves; "
+                         "D_start = copies of the initial position (SURVEY.md 8d)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -253,7 +256,21 @@ def main():
     # ---- synthetic input, generated on the device by the leaf kernel (bit-exact vs oracle: tests) ----
     d_states = torch.empty((n, 4), dtype=torch.int32, device=dev)
     leaf_lo, _ = sharding.weak_shard(n, rank)
-    eng.gen_leaves_device(n, d_states.data_ptr(), key=LEAF_KEY, first_index=leaf_lo, stream=stream)
+    if args.leaf_set == "start":
+        d_states.copy_(torch.tensor([0x00000FFF, 0xFFF00000 - (1 << 32), 0, 0], dtype=torch.int32, device=dev).expand(n, 4))
+    elif args.leaf_set == "live":
+        # D_live: draw D_ref leaves until n non-terminal ones are found (terminal = no legal move or msc >= 50)
+        got, first, chunks = 0, 2 * leaf_lo, []
+        while got < n:
+            cand = eng.gen_leaves(n, key=LEAF_KEY, first_index=first)
+            _, cnt = eng.genmoves(cand, 1)
+            live = cand[(cnt > 0) & ((cand[:, 3] >> 8) < 50)]
+            chunks.append(live)
+            got += len(live)
+            first += n
+        d_states.copy_(torch.from_numpy(np.concatenate(chunks)[:n].view(np.int32)).to(dev))
+    else:
+        eng.gen_leaves_device(n, d_states.data_ptr(), key=LEAF_KEY, first_index=leaf_lo, stream=stream)
     d_winners = torch.empty(n * reps, dtype=torch.int8, device=dev)
     d_counters = torch.zeros(4, dtype=torch.int64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
@@ -332,8 +349,10 @@ def main():
         "metric": "checkers_playouts_per_sec", "value": value, "unit": "playouts/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": "D_ref: 2^20-class random reachable leaves per GPU (reference genRandomStates recipe, seed 2016), "
-                               "%s playouts to the end, device_single-equivalent (thread-per-playout persistent lanes)" % args.mode,
+        "config": {"workload": "D_%s: %s, %s playouts to the end, device_single-equivalent (thread-per-playout persistent lanes)"
+                               % (args.leaf_set, {"ref": "2^20-class random reachable leaves per GPU (reference genRandomStates recipe, seed 2016)",
+                                                  "live": "D_ref leaves with the terminal ones rejected", "start": "copies of the initial position"}[args.leaf_set],
+                                  args.mode),
                    "leaves_per_gpu": n, "reps_per_step": reps, "playouts_per_step": playouts_per_step, "move_order": args.order,
                    "plies_per_playout": plies_per_playout, "parallelism": "leaf-sharded x%d, one 32-byte all-reduce per step" % world,
                    "l2": "256 MiB memset between timed steps (inside the timed region)", "gpu": info["name"], "sms": info["sm_count"]},

@@ -18,6 +18,7 @@
 
 #include <cmath>
 #include <cstring>
+#include <ctime>
 #include <string>
 #include <vector>
 
@@ -354,10 +355,8 @@ int b2p_tree_search(b2p_ctx *ctx, b2p_tree *t, uint32_t iterations, double secon
   std::vector<b2p_state16> leaves;
   std::vector<uint32_t> wins;
   uint64_t played = 0;
-  const double t0 = (double)clock() / CLOCKS_PER_SEC;
   struct timespec ts0;
   clock_gettime(CLOCK_MONOTONIC, &ts0);
-  (void)t0;
   for (uint32_t it = 0; iterations == 0 || it < iterations; it++) {
     if (seconds > 0) {
       struct timespec ts;
