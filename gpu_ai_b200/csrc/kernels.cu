@@ -28,6 +28,7 @@ namespace b2p {
 namespace {
 
 constexpr int kLaneBlock = 128;
+constexpr int kRatioA = 52, kRatioB = 49;  // material quotient table: numerator 0..51, denominator 0..48
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
 __device__ __forceinline__ uint32_t pick4(const Philox4 &b, int q) {
@@ -56,9 +57,13 @@ __global__ void __launch_bounds__(kLaneBlock) playout_lanes_kernel(const Playout
   constexpr int kOrder = MODE == kRandomFast ? kOrderFast : kOrderCanonical;
   constexpr uint32_t kDomain = kLeaf ? kDomainLeaf : kDomainRandom;
 
+  // heuristic mode: Gaussian quantile table + table of all material quotients a/b (a <= 51, b <= 48: 12 kings a
+  // side plus one crowning), both filled once per block; a lookup replaces an IEEE division per weight class
   __shared__ float s_gauss[kHeur ? 1025 : 1];
+  __shared__ float s_ratio[kHeur ? kRatioA * kRatioB : 1];
   if (kHeur) {
     for (int i = threadIdx.x; i < 1025; i += blockDim.x) s_gauss[i] = __uint_as_float(b2p_gauss_table_bits[i]);
+    for (int i = threadIdx.x; i < kRatioA * kRatioB; i += blockDim.x) s_ratio[i] = (float)(i / kRatioB) / (float)(i % kRatioB);
     __syncthreads();
   }
 
@@ -133,7 +138,10 @@ __global__ void __launch_bounds__(kLaneBlock) playout_lanes_kernel(const Playout
         if (res == kRunning) res = 3;  // marker: unfinished
       } else if (kHeur) {
         res = heuristic_ply(g, heur_lanes, [&](int b) { return philox_block(prm.key, pid, kDomainNoise | ((uint32_t)b << 8), ply); },
-                            [&](uint32_t r) { return gauss_lookup(s_gauss, r); });
+                            [&](uint32_t r) { return gauss_lookup(s_gauss, r); },
+                            [&](uint32_t a, uint32_t b) {
+                              return (a < (uint32_t)kRatioA && b < (uint32_t)kRatioB) ? s_ratio[a * kRatioB + b] : (float)a / (float)b;
+                            });
       } else {
         res = random_ply<kOrder>(g, pick4(rnd, q));
       }

@@ -356,8 +356,10 @@ B2P_HD bool heur_better(float w, int idx, const HeurBest &b) { return w > b.w ||
 // ptxas keeps lanes that took different rare paths apart and runs the noise scan and the index -> move
 // mapping once per sub-group (measured: 1.8 executions per ply).  `lanes` = mask of the lanes that call this
 // function together (device; ignored on the host).  No early return before the last rejoin point.
-template <class NoiseBlock, class Gauss>
-B2P_HD int heuristic_ply(Game &g, unsigned lanes, NoiseBlock &&noise_block, Gauss &&gauss) {
+// Ratio: float ratio(uint32_t a, uint32_t b) = the correctly rounded IEEE quotient float(a) / float(b)
+// (getWeight, src/heuristic.cu:44-49); the kernels serve it from a shared-memory table of all material pairs.
+template <class NoiseBlock, class Gauss, class Ratio>
+B2P_HD int heuristic_ply(Game &g, unsigned lanes, NoiseBlock &&noise_block, Gauss &&gauss, Ratio &&ratio) {
   (void)lanes;
   const Pos p = g.pos;
   const PlyMasks m = ply_masks(p);
@@ -387,8 +389,8 @@ B2P_HD int heuristic_ply(Game &g, unsigned lanes, NoiseBlock &&noise_block, Gaus
   // canonical index, which class a candidate is in: two 64-bit index masks.
   const uint32_t lo_den = m.capture ? his - 1u : his;
   const uint32_t hi_den = his >= 4u ? his - 4u : his;  // only used when a king can be captured (his >= 4 then)
-  float w0 = (float)my / (float)lo_den, w1 = (float)(my + 3u) / (float)lo_den;
-  float w2 = (float)my / (float)hi_den, w3 = (float)(my + 3u) / (float)hi_den;
+  float w0 = ratio(my, lo_den), w1 = ratio(my + 3u, lo_den);
+  float w2 = ratio(my, hi_den), w3 = ratio(my + 3u, hi_den);
   B2P_PIN_FLOAT(w0);
   B2P_PIN_FLOAT(w1);
   B2P_PIN_FLOAT(w2);
@@ -427,7 +429,7 @@ B2P_HD int heuristic_ply(Game &g, unsigned lanes, NoiseBlock &&noise_block, Gaus
       const int idx = rev ? total - 1 - i : i;
       const uint32_t promo = (((ownMen >> f) & 1u) && t >= 28) ? 3u : 0u;
       const uint32_t loss = (uint32_t)(popc(cap) + 3 * popc(cap & p.kings));
-      const float w = (float)(my + promo) / (float)(his - loss) + noise(idx);
+      const float w = ratio(my + promo, his - loss) + noise(idx);
       if (heur_better(w, idx, best)) { best.w = w; best.idx = idx; from = 1u << f; to = 1u << t; captured = cap; }
     };
     for (int i = 0; i < total && i < kLeafBuf; i++) score(i, buf_from_to[i] & 31, buf_from_to[i] >> 5, buf_captured[i]);

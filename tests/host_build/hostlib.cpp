@@ -57,7 +57,7 @@ void hb_playouts_batch(const uint32_t *packed, size_t n, uint32_t reps, uint64_t
       }
       if (mode == 1) {
         res = heuristic_ply(g, 0u, [&](int b) { return philox_block(key, pid, kDomainNoise | ((uint32_t)b << 8), ply); },
-                            [](uint32_t r) { return gauss_sigma(r); });
+                            [](uint32_t r) { return gauss_sigma(r); }, [](uint32_t a, uint32_t b) { return (float)a / (float)b; });
       } else {
         Philox4 b = philox_block(key, pid, kDomainRandom, ply >> 2);
         uint32_t r = b.v[ply & 3];
