@@ -50,8 +50,14 @@ __device__ __forceinline__ float gauss_lookup(const float *tab, uint32_t h) {
 // ---------------------------------------------------------------------------------------------
 // thread-per-playout, persistent lanes
 // ---------------------------------------------------------------------------------------------
+#ifndef B2P_HEUR_MIN_BLOCKS
+#define B2P_HEUR_MIN_BLOCKS 1  // register caps tried (6/7/8 blocks): within +-1 %, profiles/r01i_ab.txt
+#endif
+#ifndef B2P_RAND_MIN_BLOCKS
+#define B2P_RAND_MIN_BLOCKS 1
+#endif
 template <int MODE, bool LIMITED>
-__global__ void __launch_bounds__(kLaneBlock) playout_lanes_kernel(const PlayoutParams prm) {
+__global__ void __launch_bounds__(kLaneBlock, MODE == kHeuristic ? B2P_HEUR_MIN_BLOCKS : B2P_RAND_MIN_BLOCKS) playout_lanes_kernel(const PlayoutParams prm) {
   constexpr bool kHeur = MODE == kHeuristic;
   constexpr bool kLeaf = MODE == kLeafGen;
   constexpr int kOrder = MODE == kRandomFast ? kOrderFast : kOrderCanonical;
