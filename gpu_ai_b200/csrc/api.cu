@@ -101,9 +101,8 @@ unsigned int *next_slot(Device &d) { return d.d_next_ring + (d.ring_pos++ % kRin
 
 // B2P_SCHED_AUTO: warp-per-playout only pays below the batch size at which thread-per-playout
 // fills the machine's latency budget (measured on B200, profiles/: see DESIGN.md 4.5)
-// (profiles/r01d_sched_compare.jsonl: random playouts cross over between 4096 and 8192 playouts per
-// launch, heuristic playouts between 8192 and 32768)
-constexpr size_t kAutoWarpMaxRandom = 4096, kAutoWarpMaxHeuristic = 16384;
+// (profiles/r01_final_sched_compare.jsonl: both modes cross over between 4096 and 8192 playouts per launch)
+constexpr size_t kAutoWarpMaxRandom = 4096, kAutoWarpMaxHeuristic = 4096;
 bool use_warp_kernel(int sched, size_t total, KernelMode km) {
   return sched == B2P_SCHED_WARP ||
          (sched == B2P_SCHED_AUTO && total <= (km == kHeuristic ? kAutoWarpMaxHeuristic : kAutoWarpMaxRandom));

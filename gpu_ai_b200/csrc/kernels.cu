@@ -7,7 +7,8 @@
 //
 // Design (DESIGN.md has the full account):
 //  * a playout lives entirely in registers: 3 board words, turn, draw counter, ply counter;
-//    no local memory, no shared memory on the random path, no recursion, no device stack.
+//    no shared memory on the random path, no recursion; the only local memory is an 80-byte
+//    sequence buffer touched by the rare king multi-jump enumeration (~1 % of plies).
 //  * persistent lanes: every lane of every resident warp owns one playout at a time; finished
 //    lanes are refilled together, once every 4 plies, with ONE warp-aggregated atomicAdd on the
 //    work-queue head (__ballot_sync + __popc prefix) -- the same point where all lanes draw their
@@ -15,6 +16,9 @@
 //  * the only global traffic is one coalesced LDG.128 per playout and one STG.8 per result.
 //  * integer work only (LOP3 / SHF / IADD3 / POPC / IMAD); no tensor cores: nothing here is a
 //    contraction.
+//  * SIMT discipline (measured): nothing lane-dependent branches BEFORE the common
+//    selection path -- rare work (multi-jump enumeration, publishing a result) comes after it or is
+//    written branch-free; the heuristic ply is staged with explicit rejoin points.
 #include "kernels.cuh"
 
 #include "bitboard.cuh"
