@@ -306,3 +306,32 @@ def test_run_counts_equals_winner_tally(engine):
         w = w.reshape(6, n)
         assert np.array_equal(wins[:, 0], (w == 0).sum(axis=0)) and np.array_equal(wins[:, 1], (w == 1).sum(axis=0))
         assert np.array_equal(c, c2)
+
+
+# ---- in-process multi-device sharding (needs >= 2 visible GPUs; skipped on a 1-GPU box) --------------------------
+def test_in_process_multi_device_equals_single_device(engine):
+    import torch
+    import gpu_ai_b200 as b
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    multi = b.Engine(devices=torch.cuda.device_count(), seed=12345)
+    st = np.concatenate([engine.gen_leaves(70001, key=12), fast_synthetic(10000, 29)])
+    assert np.array_equal(multi.gen_leaves(70001, key=12), st[:70001])
+    for mode, order in ((MODE_RANDOM, ORDER_FAST), (MODE_HEURISTIC, ORDER_CANONICAL)):
+        a = engine.run_packed(st, reps=3, key=6, pid_base=40, mode=mode, order=order, want_plies=True, want_final=True)
+        c = multi.run_packed(st, reps=3, key=6, pid_base=40, mode=mode, order=order, want_plies=True, want_final=True)
+        for x, y in zip(a, c):
+            assert np.array_equal(x, y)
+        wa, ca = engine.run_counts(st, reps=5, key=7, mode=mode, order=order)
+        wc, cc = multi.run_counts(st, reps=5, key=7, mode=mode, order=order)
+        assert np.array_equal(wa, wc) and np.array_equal(ca, cc)
+    ma, na = engine.genmoves(st, 40)
+    mc, nc = multi.genmoves(st, 40)
+    assert np.array_equal(ma, mc) and np.array_equal(na, nc)
+    s776 = b.engine.unpack776(st)
+    e1, e2 = b.Engine(devices=1, seed=99), b.Engine(devices=torch.cuda.device_count(), seed=99)
+    assert np.array_equal(e1.run_states776(s776), e2.run_states776(s776))
+    t1, t2 = b.Tree(START_PACKED), b.Tree(START_PACKED)
+    t1.search(engine, iterations=6, initial_batch=3000, reps=4, key=2)
+    t2.search(multi, iterations=6, initial_batch=3000, reps=4, key=2)
+    assert np.array_equal(t1.root_moves()[1], t2.root_moves()[1]) and np.array_equal(t1.root_moves()[2], t2.root_moves()[2])
