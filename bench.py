@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--leaf-set", default="ref", choices=["ref", "live", "start"],
                     help="D_ref = genRandomStates recipe (default, 36 %% terminal); D_live = D_ref without terminal leaves; "
                          "D_start = copies of the initial position (SURVEY.md 8d)")
+    ap.add_argument("--ref-seconds", type=float, default=0.0,
+                    help="--impl reference: CPU seconds per step (0 = automatic: bounded so that the whole run ends within minutes)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -198,7 +200,7 @@ def run_reference_arm(args):
     from oracle import pyoracle
     chk = pyoracle.Checker("port")
     leaves = chk.gen_leaves(1 << 17, key=LEAF_KEY)   # bounded sample of the same D_ref workload
-    per_step_budget = max(1.0, min(12.0, 150.0 / max(1, args.steps + args.warmup)))
+    per_step_budget = args.ref_seconds if args.ref_seconds > 0 else max(1.0, min(12.0, 150.0 / max(1, args.steps + args.warmup)))
     base, n, _ = cpu_playouts_per_s(leaves, args.mode, budget_s=per_step_budget)
     from oracle import pyoracle as po
     if po.have_reference():
