@@ -42,12 +42,19 @@ __device__ __forceinline__ uint32_t pick4(const Philox4 &b, int q) {
   return r;
 }
 
-// 16-bit draw -> N(0, 0.11^2): 10-bit quantile bucket + 6-bit linear interpolation (one fma)
-__device__ __forceinline__ float gauss_lookup(const float *tab, uint32_t h) {
-  const uint32_t i = (h >> 6) & 1023u;
-  const float frac = (float)(h & 63u) * (1.0f / 64.0f);
-  const float lo = tab[i], hi = tab[i + 1];
-  return __fmaf_rn(hi - lo, frac, lo);
+// 16-bit draw -> N(0, 0.11^2): 10-bit quantile bucket + 6-bit linear interpolation (one fma).
+// The shared table holds {T[i], (T[i+1] - T[i]) / 64}: fma(d / 64, k, lo) is bit-identical to the protocol's
+// fma(d, k / 64, lo) (power-of-two scaling is exact), and costs one LDS.64 instead of two loads and a subtract.
+__device__ __forceinline__ float gauss_lookup(const float2 *tab, uint32_t h) {
+  const float2 v = tab[(h >> 6) & 1023u];
+  return __fmaf_rn(v.y, (float)(h & 63u), v.x);
+}
+
+__device__ __forceinline__ void fill_gauss_table(float2 *tab) {
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
+    const float lo = __uint_as_float(b2p_gauss_table_bits[i]), hi = __uint_as_float(b2p_gauss_table_bits[i + 1]);
+    tab[i] = make_float2(lo, (hi - lo) * (1.0f / 64.0f));
+  }
 }
 
 // exclusive prefix sum of c over the lanes + total
@@ -116,7 +123,7 @@ __device__ __forceinline__ void consider(Best &b, float w, int idx, uint32_t fro
   if (w > b.w || (w == b.w && idx < b.idx)) { b.w = w; b.idx = idx; b.from = from; b.to = to; b.captured = captured; }
 }
 
-__device__ __forceinline__ int warp_heuristic_ply(Game &g, uint64_t key, uint64_t pid, uint32_t ply, const float *gauss,
+__device__ __forceinline__ int warp_heuristic_ply(Game &g, uint64_t key, uint64_t pid, uint32_t ply, const float2 *gauss,
                                                   unsigned lane) {
   if (g.msc >= kDrawPlies) return -1;
   const Pos p = g.pos;
@@ -198,9 +205,9 @@ template <int MODE>
 __global__ void __launch_bounds__(kWarpBlock) playout_warp_kernel(const PlayoutParams prm) {
   constexpr bool kHeur = MODE == kHeuristic;
   constexpr int kOrder = MODE == kRandomFast ? kOrderFast : kOrderCanonical;
-  __shared__ float s_gauss[kHeur ? 1025 : 1];
+  __shared__ float2 s_gauss[kHeur ? 1024 : 1];
   if (kHeur) {
-    for (int i = threadIdx.x; i < 1025; i += blockDim.x) s_gauss[i] = __uint_as_float(b2p_gauss_table_bits[i]);
+    fill_gauss_table(s_gauss);
     __syncthreads();
   }
   const unsigned lane = threadIdx.x & 31u;
