@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(kLaneBlock, MODE == kHeuristic ? B2P_HEUR_MIN_
         if (w < prm.total) {
           uint32_t leaf = w, rep = 0;
           if (prm.total != prm.n) {
-            rep = w / prm.n;
+            rep = prm.div_shift != 0xFFFFFFFFu ? (__umulhi(w, prm.div_magic) >> prm.div_shift) : w / prm.n;
             leaf = w - rep * prm.n;
           }
           pid = prm.pid_base + (uint64_t)rep * prm.rep_stride + leaf;
@@ -218,7 +218,9 @@ __global__ void __launch_bounds__(128) genmoves_kernel(const uint4 *__restrict__
 }
 
 template <int MODE, bool LIMITED>
-cudaError_t launch_lanes_t(const PlayoutParams &prm, int sm_count, cudaStream_t stream, LaunchInfo *info) {
+cudaError_t launch_lanes_t(const PlayoutParams &prm_in, int sm_count, cudaStream_t stream, LaunchInfo *info) {
+  PlayoutParams prm = prm_in;
+  set_divider(prm);
   auto kern = playout_lanes_kernel<MODE, LIMITED>;
   int per_sm = 0;
   cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kLaneBlock, 0);

@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(kWarpBlock) playout_warp_kernel(const PlayoutP
   for (uint32_t w = gwarp; w < prm.total; w += nwarps) {
     uint32_t leaf = w, rep = 0;
     if (prm.total != prm.n) {
-      rep = w / prm.n;
+      rep = prm.div_shift != 0xFFFFFFFFu ? (__umulhi(w, prm.div_magic) >> prm.div_shift) : w / prm.n;
       leaf = w - rep * prm.n;
     }
     const uint64_t pid = prm.pid_base + (uint64_t)rep * prm.rep_stride + leaf;
@@ -268,7 +268,9 @@ __global__ void __launch_bounds__(kWarpBlock) playout_warp_kernel(const PlayoutP
 }
 
 template <int MODE>
-cudaError_t launch_warp_t(const PlayoutParams &prm, int sm_count, cudaStream_t stream, LaunchInfo *info) {
+cudaError_t launch_warp_t(const PlayoutParams &prm_in, int sm_count, cudaStream_t stream, LaunchInfo *info) {
+  PlayoutParams prm = prm_in;
+  set_divider(prm);
   auto kern = playout_warp_kernel<MODE>;
   int per_sm = 0;
   cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWarpBlock, 0);
