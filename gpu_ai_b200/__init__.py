@@ -20,6 +20,7 @@ from .engine import (  # noqa: F401
     lib_path,
     load_library,
 )
+from .players import B200MCTSPlayer, Player  # noqa: F401
 from .drivers import (  # noqa: F401
     DeviceCoarsePlayoutDriver,
     DeviceHeuristicPlayoutDriver,
@@ -33,5 +34,5 @@ __all__ = [
     "B2PError", "Engine", "Tree", "load_library", "lib_path",
     "MODE_RANDOM", "MODE_HEURISTIC", "SCHED_THREAD", "SCHED_WARP", "SCHED_AUTO", "ORDER_CANONICAL", "ORDER_FAST",
     "PlayoutDriver", "DeviceSinglePlayoutDriver", "DeviceMultiplePlayoutDriver", "DeviceCoarsePlayoutDriver",
-    "DeviceHeuristicPlayoutDriver", "getPlayoutDriver",
+    "DeviceHeuristicPlayoutDriver", "getPlayoutDriver", "Player", "B200MCTSPlayer",
 ]

@@ -335,3 +335,24 @@ def test_in_process_multi_device_equals_single_device(engine):
     t1.search(engine, iterations=6, initial_batch=3000, reps=4, key=2)
     t2.search(multi, iterations=6, initial_batch=3000, reps=4, key=2)
     assert np.array_equal(t1.root_moves()[1], t2.root_moves()[1]) and np.array_equal(t1.root_moves()[2], t2.root_moves()[2])
+
+
+def test_b200_mcts_player_plays_legal_moves(engine, port):
+    """Player-interface mirror: a short game of the B200 searcher against uniformly random replies."""
+    import gpu_ai_b200 as b
+    rng = np.random.default_rng(3)
+    me = b.B200MCTSPlayer(engine=engine, seconds=0.05, initial_batch=2048, reps=8)
+    me.start()
+    state_tree = b.Tree(START_PACKED)   # the arbiter's copy of the game
+    for ply in range(24):
+        info = state_tree.info()
+        state = info["root_state"]
+        if info["root_moves"] == 0 or (state[3] >> 8) >= 50:
+            break
+        legal, cnt = port.genmoves(state.reshape(1, 4), 64)
+        legal = [int(x) for x in legal[0, :cnt[0]]]
+        mv = me.getMove(state, verbose=False) if ply % 2 == 0 else legal[int(rng.integers(len(legal)))]
+        assert mv in legal
+        me.move(mv)
+        state_tree.move(mv)
+    assert me.playouts > 0 and me.getName() == "mcts_b200"
