@@ -128,3 +128,26 @@ def test_update_counts_equals_update_with_winners():
         assert a.info()["total_trials"] == c.info()["total_trials"] and a.info()["wins"] == c.info()["wins"]
         for x, y in zip(a.root_moves(), c.root_moves()):
             assert np.array_equal(x, y)
+
+
+def test_tree_equals_reference_gametree_random_roots(ref, golden):
+    """randomised sessions: reachable roots from the golden leaf set, random batch schedules, random re-rooting"""
+    import gpu_ai_b200 as b
+    rng = np.random.default_rng(17)
+    roots = golden["leaves_states"][golden["leaves_counts"] > 0]
+    for trial in range(12):
+        root = roots[int(rng.integers(len(roots)))]
+        batches = [int(x) for x in rng.choice([0, 1, 2, 3, 17, 50, 120, 700, 2500], size=10)]
+        moves_after = tuple(sorted(int(x) for x in rng.choice(np.arange(2, 9), size=2, replace=False)))
+        mine, theirs = b.Tree(root), RefTree(ref, root)
+        try:
+            a = drive(mine, batches, salt=100 + trial, moves_after=moves_after)
+        except b.B2PError:
+            a = None   # best_move on an unexpanded root: the reference asserts there (src/mcts.cpp:40)
+        if a is None:
+            continue
+        c = drive(theirs, batches, salt=100 + trial, moves_after=moves_after)
+        assert len(a) == len(c)
+        for x, y in zip(a, c):
+            assert x.shape == y.shape and np.array_equal(x, y)
+        assert mine.info()["total_trials"] == theirs.total()
