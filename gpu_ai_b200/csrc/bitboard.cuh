@@ -227,7 +227,36 @@ B2P_HD int select_dir_major(const uint32_t a[4], int n0, int n1, int n2, int k) 
   return select_bit(m, k) | (slot << 5);
 }
 
+// Experiment B2P_SELECT2 (not yet measured on a GPU; same result, tests/host_build checks it against the search
+// below on random masks): two levels -- the byte (two board rows) from three independent prefix counts, then a
+// peel over the few origins inside that byte -- instead of five dependent search steps.
+B2P_HD int select_origin_major_two_level(const uint32_t a[4], int k) {
+  const int c8 = popc(a[0] & 0xFFu) + popc(a[1] & 0xFFu) + popc(a[2] & 0xFFu) + popc(a[3] & 0xFFu);
+  const int c16 = popc(a[0] & 0xFFFFu) + popc(a[1] & 0xFFFFu) + popc(a[2] & 0xFFFFu) + popc(a[3] & 0xFFFFu);
+  const int c24 = popc(a[0] & 0xFFFFFFu) + popc(a[1] & 0xFFFFFFu) + popc(a[2] & 0xFFFFFFu) + popc(a[3] & 0xFFFFFFu);
+  const int byte = (k >= c8) + (k >= c16) + (k >= c24);
+  k -= byte == 0 ? 0 : byte == 1 ? c8 : byte == 2 ? c16 : c24;
+  const int shift = 8 * byte;
+  const uint32_t x0 = (a[0] >> shift) & 0xFFu, x1 = (a[1] >> shift) & 0xFFu, x2 = (a[2] >> shift) & 0xFFu, x3 = (a[3] >> shift) & 0xFFu;
+  uint32_t u = x0 | x1 | x2 | x3, bit = 0;
+  for (;;) {
+    bit = u & (0u - u);
+    const int cnt = ((x0 & bit) != 0) + ((x1 & bit) != 0) + ((x2 & bit) != 0) + ((x3 & bit) != 0);
+    if (k < cnt || u == 0) break;
+    k -= cnt;
+    u ^= bit;
+  }
+  uint32_t t = ((x0 & bit) ? 1u : 0u) | ((x1 & bit) ? 2u : 0u) | ((x2 & bit) ? 4u : 0u) | ((x3 & bit) ? 8u : 0u);
+  if (k >= 1) t &= t - 1;
+  if (k >= 2) t &= t - 1;
+  if (k >= 3) t &= t - 1;
+  return (lowbit(bit | 0x100u) + shift) | (lowbit(t | 16u) << 5);
+}
+
 B2P_HD int select_origin_major(const uint32_t a[4], int k) {
+#if defined(B2P_SELECT2)
+  return select_origin_major_two_level(a, k);
+#endif
   // binary search for the origin o with  count(origins < o) <= k < count(origins <= o)
   int lo = 0, below = 0;
 #if defined(__CUDA_ARCH__)

@@ -90,6 +90,23 @@ void hb_gen_leaves(size_t n, uint64_t key, uint64_t first_index, uint32_t *packe
   }
 }
 
+// experiment check: the two-level origin-major select returns the same (origin, slot) as the binary search
+uint64_t hb_select_mismatches(uint64_t seed, uint64_t trials) {
+  uint64_t bad = 0, x = seed * 0x9E3779B97F4A7C15ull + 1;
+  auto next = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
+  for (uint64_t t = 0; t < trials; t++) {
+    uint32_t a[4];
+    const uint64_t density = next() % 5;
+    for (int d = 0; d < 4; d++) {
+      a[d] = (uint32_t)next();
+      for (uint64_t r = 0; r < density; r++) a[d] &= (uint32_t)next();
+    }
+    const int n = popc(a[0]) + popc(a[1]) + popc(a[2]) + popc(a[3]);
+    for (int k = 0; k < n; k++) bad += select_origin_major(a, k) != select_origin_major_two_level(a, k);
+  }
+  return bad;
+}
+
 void hb_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
   Philox4 o = philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1]);
   for (int i = 0; i < 4; i++) out[i] = o.v[i];

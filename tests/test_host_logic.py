@@ -86,3 +86,10 @@ def test_bitboard_movelists_hypothesis(hostbuild, port):
         assert c1[0] == c2[0] and np.array_equal(m1, m2)
 
     check()
+
+
+def test_two_level_select_experiment_matches(hostbuild):
+    """B2P_SELECT2 candidate (bitboard.cuh): same (origin, slot) as the shipped origin-major search on random masks"""
+    f = hostbuild.lib.hb_select_mismatches
+    f.restype = C.c_uint64
+    assert f(C.c_uint64(7), C.c_uint64(200000)) == 0
