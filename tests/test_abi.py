@@ -91,3 +91,14 @@ def test_product_does_not_reference_oracle():
                 txt = open(os.path.join(base, f), errors="ignore").read()
                 assert "pyoracle" not in txt and "liboracle" not in txt and "checkers_oracle" not in txt, f
                 assert not re.search(r'#include\s+"[^"]*oracle/', txt), f
+
+
+def test_missing_extension_fails_loudly():
+    """No silent fallback: if libb2p.so is not there, importing the engine and creating anything raises."""
+    import subprocess
+    import sys
+    code = ("import os, sys; sys.path.insert(0, %r); os.environ['B2P_LIB_PATH'] = '/nonexistent/libb2p.so'\n"
+            "import gpu_ai_b200 as b\n"
+            "try:\n    b.load_library()\nexcept b.B2PError as e:\n    print('RAISED', 'no CPU fallback' in str(e).lower() or 'missing' in str(e))\n" % ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert "RAISED True" in r.stdout, r.stdout + r.stderr
