@@ -14,6 +14,9 @@
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <memory>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -45,6 +48,74 @@ struct Device {
   Buffer h_states, h_winners, h_misc;  // pinned staging
   unsigned int *d_next_ring = nullptr;  // kRing work-queue heads, rotated per launch
   unsigned ring_pos = 0;  // advanced under the caller's serialisation (one caller per context)
+  // one event per ring slot, recorded behind the launch that uses the slot: a slot is only handed out again
+  // after that launch has finished, whatever stream it ran on (launches may sit on caller-supplied streams)
+  std::vector<cudaEvent_t> ring_ev;
+  std::vector<char> ring_busy;
+  unsigned next_aux = 0;  // round-robin over `aux` per DEVICE (segments of b2p_run_states776)
+};
+
+// Persistent host workers of a context (packing 776-byte States, widening results): created on first use,
+// parked on a condition variable between calls.  The reference-facing call used to spawn std::threads per call.
+class Pool {
+ public:
+  ~Pool() {
+    {
+      std::lock_guard<std::mutex> l(mu_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    for (auto &t : th_) t.join();
+  }
+  // runs f() on `workers` threads in total (the caller is one of them); returns when all have returned
+  void run(size_t workers, const std::function<void()> &f) {
+    const unsigned hw = std::thread::hardware_concurrency();
+    const size_t cap = std::min<size_t>(hw ? hw : 1, 32);
+    workers = std::min(workers, cap);
+    if (workers <= 1) {
+      f();
+      return;
+    }
+    const size_t helpers = workers - 1;
+    {
+      std::lock_guard<std::mutex> l(mu_);
+      while (th_.size() < helpers) th_.emplace_back([this, id = th_.size()] { loop(id); });
+      job_ = &f;
+      want_ = helpers;
+      pending_ = helpers;
+      gen_++;
+    }
+    cv_.notify_all();
+    f();
+    std::unique_lock<std::mutex> l(mu_);
+    done_.wait(l, [this] { return pending_ == 0; });
+    job_ = nullptr;
+  }
+
+ private:
+  void loop(size_t id) {
+    uint64_t seen = 0;
+    for (;;) {
+      const std::function<void()> *job = nullptr;
+      {
+        std::unique_lock<std::mutex> l(mu_);
+        cv_.wait(l, [&] { return stop_ || (gen_ != seen && id < want_); });
+        if (stop_) return;
+        seen = gen_;
+        job = job_;
+      }
+      (*job)();
+      std::lock_guard<std::mutex> l(mu_);
+      if (--pending_ == 0) done_.notify_one();
+    }
+  }
+  std::vector<std::thread> th_;
+  std::mutex mu_;
+  std::condition_variable cv_, done_;
+  const std::function<void()> *job_ = nullptr;
+  size_t want_ = 0, pending_ = 0;
+  uint64_t gen_ = 0;
+  bool stop_ = false;
 };
 
 }  // namespace
@@ -55,6 +126,7 @@ struct b2p_ctx {
   uint64_t calls = 0;
   std::atomic<uint64_t> launches{0};
   std::string err;
+  Pool pool;
 };
 
 namespace {
@@ -97,7 +169,6 @@ void release(Buffer &b) {
 }
 
 constexpr unsigned kRing = 256;
-unsigned int *next_slot(Device &d) { return d.d_next_ring + (d.ring_pos++ % kRing); }
 
 // B2P_SCHED_AUTO: warp-per-playout only pays below the batch size at which thread-per-playout
 // fills the machine's latency budget (measured on B200, profiles/: see DESIGN.md 4.5)
@@ -106,6 +177,22 @@ constexpr size_t kAutoWarpMaxRandom = 4096, kAutoWarpMaxHeuristic = 4096;
 bool use_warp_kernel(int sched, size_t total, KernelMode km) {
   return sched == B2P_SCHED_WARP ||
          (sched == B2P_SCHED_AUTO && total <= (km == kHeuristic ? kAutoWarpMaxHeuristic : kAutoWarpMaxRandom));
+}
+
+// One playout launch on device `d`: takes the next work-queue head of the ring (waiting, if the ring has
+// wrapped, for the launch that last used it -- so any number of launches may be in flight on any streams),
+// launches, and records the slot's event behind the kernel.
+cudaError_t launch_playouts(b2p_ctx *ctx, Device &d, PlayoutParams &prm, KernelMode km, int sched, cudaStream_t st) {
+  const unsigned slot = d.ring_pos++ % kRing;
+  cudaError_t e;
+  if (d.ring_busy[slot] && (e = cudaEventSynchronize(d.ring_ev[slot])) != cudaSuccess) return e;
+  prm.next = d.d_next_ring + slot;
+  e = use_warp_kernel(sched, prm.total, km) ? launch_playout_warp(prm, km, d.sm_count, st, nullptr)
+                                            : launch_playout_lanes(prm, km, d.sm_count, st, nullptr);
+  if (e != cudaSuccess) return e;
+  ctx->launches++;
+  d.ring_busy[slot] = 1;
+  return cudaEventRecord(d.ring_ev[slot], st);
 }
 
 bool mode_to_kernel(int mode, int order, KernelMode *out) {
@@ -187,6 +274,17 @@ void parallel_for(size_t n, size_t grain, F &&f) {
   for (auto &t : th) t.join();
 }
 
+// sharding policy of the host-buffer calls: a second device is only used once every shard keeps at least
+// kMinShard playouts (a 50-leaf MCTS batch spread over 8 GPUs costs 8 copies and 8 launches for nothing:
+// measured 0.46 ms vs 0.10 ms, profiles/r01x_sweep_tests_sh_protocol_8gpu.jsonl)
+constexpr size_t kMinShard = 8192;
+constexpr size_t kPackGrain = 512;    // reference States per host pack task (400 KB of `State`s, ~35 us)
+constexpr size_t kSegmentMin = 8192, kSegmentMax = 32768;  // leaves per launch of the 776-byte pipeline
+int device_span(const b2p_ctx *ctx, size_t n, size_t work) {
+  const size_t by_work = std::max<size_t>(1, work / kMinShard);
+  return (int)std::min(std::min(ctx->devs.size(), n), by_work);
+}
+
 struct Shard {
   size_t lo, hi;
 };
@@ -234,6 +332,15 @@ int b2p_create(b2p_ctx **out, const int *device_ids, int n_dev, uint64_t seed) {
       return fail(nullptr, B2P_ENODEV, std::string("b2p_create: device ") + prop.name + " is not sm_100 class; the kernels are built for sm_100a only");
     }
     d.sm_count = prop.multiProcessorCount;
+    d.ring_ev.assign(kRing, nullptr);
+    d.ring_busy.assign(kRing, 0);
+    for (cudaEvent_t &ev : d.ring_ev)
+      if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) break;
+    if (e != cudaSuccess) {
+      ctx->devs.push_back(d);
+      b2p_destroy(ctx);
+      return fail(nullptr, B2P_ECUDA, std::string("b2p_create: ") + cudaGetErrorString(e));
+    }
     for (cudaStream_t &a : d.aux)
       if (cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking) != cudaSuccess) a = nullptr;
     ctx->devs.push_back(d);
@@ -248,6 +355,10 @@ void b2p_destroy(b2p_ctx *ctx) {
     if (d.id < 0) continue;
     cudaSetDevice(d.id);
     if (d.stream) cudaStreamSynchronize(d.stream);
+    for (cudaStream_t a : d.aux)
+      if (a) cudaStreamSynchronize(a);
+    for (cudaEvent_t ev : d.ring_ev)
+      if (ev) cudaEventDestroy(ev);
     for (Buffer *b : {&d.d_states, &d.d_winners, &d.d_plies, &d.d_final, &d.d_moves, &d.d_counts, &d.d_misc, &d.h_states, &d.h_winners, &d.h_misc}) release(*b);
     if (d.d_next_ring) cudaFree(d.d_next_ring);
     if (d.ev0) cudaEventDestroy(d.ev0);
@@ -287,6 +398,24 @@ int b2p_sync(b2p_ctx *ctx) {
     B2P_CUDA(ctx, cudaStreamSynchronize(d.stream));
   }
   return B2P_OK;
+}
+
+// ---- caller-visible pinned host memory -----------------------------------------------------------------
+int b2p_alloc_host(void **out, size_t bytes) {
+  if (!out) return B2P_EINVAL;
+  *out = nullptr;
+  if (bytes == 0) return B2P_OK;
+  const cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocPortable);
+  if (e != cudaSuccess) {
+    *out = nullptr;
+    return fail(nullptr, e == cudaErrorMemoryAllocation ? B2P_ENOMEM : B2P_ECUDA, std::string("b2p_alloc_host: ") + cudaGetErrorString(e));
+  }
+  return B2P_OK;
+}
+
+int b2p_free_host(void *ptr) {
+  if (!ptr) return B2P_OK;
+  return cudaFreeHost(ptr) == cudaSuccess ? B2P_OK : B2P_ECUDA;
 }
 
 // ---- converters ------------------------------------------------------------------------------------
@@ -359,12 +488,8 @@ int b2p_run_packed_device(b2p_ctx *ctx, int dev_index, const b2p_state16 *d_stat
   prm.plies = d_plies;
   prm.final_states = reinterpret_cast<uint4 *>(d_final);
   prm.counters = reinterpret_cast<unsigned long long *>(d_counters);
-  prm.next = next_slot(d);
-  cudaError_t e;
-  if (use_warp_kernel(sched, (size_t)n * reps, km)) e = launch_playout_warp(prm, km, d.sm_count, st, nullptr);
-  else e = launch_playout_lanes(prm, km, d.sm_count, st, nullptr);
+  const cudaError_t e = launch_playouts(ctx, d, prm, km, sched, st);
   if (e != cudaSuccess) return fail(ctx, B2P_ECUDA, std::string("playout launch: ") + cudaGetErrorString(e));
-  ctx->launches++;
   return B2P_OK;
 }
 
@@ -402,10 +527,8 @@ int b2p_gen_leaves_device(b2p_ctx *ctx, int dev_index, size_t n, uint64_t key, u
   prm.pid_base = first_index;
   prm.max_plies = 0;
   prm.final_states = reinterpret_cast<uint4 *>(d_out);
-  prm.next = next_slot(d);
-  cudaError_t e = launch_playout_lanes(prm, kLeafGen, d.sm_count, st, nullptr);
+  const cudaError_t e = launch_playouts(ctx, d, prm, kLeafGen, B2P_SCHED_THREAD, st);
   if (e != cudaSuccess) return fail(ctx, B2P_ECUDA, std::string("leafgen launch: ") + cudaGetErrorString(e));
-  ctx->launches++;
   return B2P_OK;
 }
 
@@ -419,7 +542,7 @@ int b2p_run_packed(b2p_ctx *ctx, const b2p_state16 *states, size_t n, uint32_t r
   if (!states) return fail(ctx, B2P_EINVAL, "states is NULL");
   KernelMode km;
   if (!mode_to_kernel(mode, order, &km)) return fail(ctx, B2P_EINVAL, "unknown mode/order");
-  const int G = (int)std::min<size_t>(ctx->devs.size(), n);
+  const int G = device_span(ctx, n, n * (size_t)reps);
   // phase 1: enqueue everything on every device (copies and kernels are asynchronous)
   for (int g = 0; g < G; g++) {
     Device &d = ctx->devs[g];
@@ -449,11 +572,8 @@ int b2p_run_packed(b2p_ctx *ctx, const b2p_state16 *states, size_t n, uint32_t r
     prm.plies = plies_out ? (uint32_t *)d.d_plies.ptr : nullptr;
     prm.final_states = final_out ? (uint4 *)d.d_final.ptr : nullptr;
     prm.counters = (unsigned long long *)d.d_misc.ptr;
-    prm.next = next_slot(d);
-    cudaError_t e = use_warp_kernel(sched, prm.total, km) ? launch_playout_warp(prm, km, d.sm_count, d.stream, nullptr)
-                                                      : launch_playout_lanes(prm, km, d.sm_count, d.stream, nullptr);
+    const cudaError_t e = launch_playouts(ctx, d, prm, km, sched, d.stream);
     if (e != cudaSuccess) return fail(ctx, B2P_ECUDA, std::string("playout launch: ") + cudaGetErrorString(e));
-    ctx->launches++;
     // gather: device layout [rep][local leaf] -> host layout [rep][global leaf]
     if (winners_out)
       B2P_CUDA(ctx, cudaMemcpy2DAsync(winners_out + sh.lo, n, d.d_winners.ptr, nl, nl, reps, cudaMemcpyDeviceToHost, d.stream));
@@ -484,7 +604,7 @@ int b2p_run_counts(b2p_ctx *ctx, const b2p_state16 *states, size_t n, uint32_t r
   if (!states || !wins_out) return fail(ctx, B2P_EINVAL, "NULL buffer");
   KernelMode km;
   if (!mode_to_kernel(mode, order, &km)) return fail(ctx, B2P_EINVAL, "unknown mode/order");
-  const int G = (int)std::min<size_t>(ctx->devs.size(), n);
+  const int G = device_span(ctx, n, n * (size_t)reps);
   for (int g = 0; g < G; g++) {
     Device &d = ctx->devs[g];
     const Shard sh = shard_of(n, g, G);
@@ -510,11 +630,8 @@ int b2p_run_counts(b2p_ctx *ctx, const b2p_state16 *states, size_t n, uint32_t r
     prm.max_plies = -1;
     prm.leaf_wins = (unsigned int *)d.d_plies.ptr;
     prm.counters = (unsigned long long *)d.d_misc.ptr;
-    prm.next = next_slot(d);
-    cudaError_t e = use_warp_kernel(sched, prm.total, km) ? launch_playout_warp(prm, km, d.sm_count, d.stream, nullptr)
-                                                      : launch_playout_lanes(prm, km, d.sm_count, d.stream, nullptr);
+    const cudaError_t e = launch_playouts(ctx, d, prm, km, sched, d.stream);
     if (e != cudaSuccess) return fail(ctx, B2P_ECUDA, std::string("playout launch: ") + cudaGetErrorString(e));
-    ctx->launches++;
     B2P_CUDA(ctx, cudaMemcpyAsync(wins_out + 2 * sh.lo, d.d_plies.ptr, nl * 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, d.stream));
     B2P_CUDA(ctx, cudaMemcpyAsync(d.h_misc.ptr, d.d_misc.ptr, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, d.stream));
   }
@@ -535,17 +652,24 @@ int b2p_run_states776(b2p_ctx *ctx, const void *states, size_t n, int mode, int 
   if (mode != B2P_MODE_RANDOM && mode != B2P_MODE_HEURISTIC) return fail(ctx, B2P_EINVAL, "unknown mode");
   const uint64_t key = ctx->seed + 0x9E3779B97F4A7C15ull * ctx->calls;
   ctx->calls++;
-  const int G = (int)std::min<size_t>(ctx->devs.size(), n);
+  const int G = device_span(ctx, n, n);
   const unsigned char *src = (const unsigned char *)states;
   const KernelMode km = mode == B2P_MODE_HEURISTIC ? kHeuristic : kRandomFast;
 
-  // Chunk pipeline: host threads pack 776 B -> 16 B straight into pinned staging (48x less PCIe
-  // traffic than the reference's raw State copy); as soon as a chunk is packed its H2D copy,
-  // kernel and D2H copy are queued on one of the device's streams, so the GPU work of chunk c
-  // hides behind the packing of chunk c+1.  Playout ids are global, so chunking changes nothing.
-  struct Chunk { int g; size_t lo, len; };
-  std::vector<Chunk> chunks;
-  const size_t kChunk = n <= (1u << 16) ? n : (1u << 15);
+  // Two granularities.  PACK tasks (kPackGrain states) are what the host
+  // workers pull: even a 2 k-leaf MCTS batch is packed by several cores.  LAUNCH segments (kSegment leaves)
+  // are what the GPU sees: the worker that packs the last task of a segment queues the segment's H2D copy,
+  // kernel and D2H copy on one of the device's streams, so the GPU work of segment s hides behind the
+  // packing of segment s+1 and no launch is smaller than it has to be.  Packing goes 776 B -> 16 B straight
+  // into pinned staging (48x less PCIe traffic than the reference's raw State copy).  Playout ids are
+  // global leaf indices, so neither granularity changes any result.
+  // a quarter of the batch per launch, within [8192, 32768]: mid-size batches (the MCTS range 2 k - 65 k) still
+  // overlap packing with GPU work, large ones do not pay for more launches than they need
+  const size_t kSegment = std::min(kSegmentMax, std::max(kSegmentMin, (n / 4 + kPackGrain - 1) / kPackGrain * kPackGrain));
+  struct Segment { int g; size_t lo, len; std::atomic<int> todo; };
+  struct Task { int seg; size_t lo, len; };
+  std::vector<std::unique_ptr<Segment>> segs;
+  std::vector<Task> tasks;
   for (int g = 0; g < G; g++) {
     Device &d = ctx->devs[g];
     const Shard sh = shard_of(n, g, G);
@@ -557,73 +681,97 @@ int b2p_run_states776(b2p_ctx *ctx, const void *states, size_t n, int mode, int 
     if ((rc = ensure(ctx, d.d_states, nl * sizeof(b2p_state16), false))) return rc;
     if ((rc = ensure(ctx, d.d_winners, nl, false))) return rc;
     if ((rc = ensure(ctx, d.h_winners, nl, true))) return rc;
-    for (size_t lo = 0; lo < nl; lo += kChunk) chunks.push_back({g, lo, std::min(kChunk, nl - lo)});
+    // the tail is merged into the last segment when it is short (no 100-leaf launches)
+    for (size_t lo = 0; lo < nl;) {
+      size_t len = std::min(kSegment, nl - lo);
+      if (nl - lo - len < kSegment / 4) len = nl - lo;
+      auto sg = std::make_unique<Segment>();
+      sg->g = g; sg->lo = lo; sg->len = len;
+      sg->todo.store((int)((len + kPackGrain - 1) / kPackGrain));
+      segs.push_back(std::move(sg));
+      lo += len;
+    }
   }
   // interleave devices so that every GPU gets work early
-  std::stable_sort(chunks.begin(), chunks.end(), [](const Chunk &a, const Chunk &b) { return a.lo < b.lo; });
+  std::stable_sort(segs.begin(), segs.end(), [](const std::unique_ptr<Segment> &a, const std::unique_ptr<Segment> &b) { return a->lo < b->lo; });
+  for (size_t s = 0; s < segs.size(); s++)
+    for (size_t lo = 0; lo < segs[s]->len; lo += kPackGrain) tasks.push_back({(int)s, lo, std::min(kPackGrain, segs[s]->len - lo)});
 
-  std::atomic<size_t> next_chunk{0};
+  std::atomic<size_t> next_task{0};
   std::mutex enqueue_mu;
   std::string err;
   auto worker = [&]() {
     for (;;) {
-      const size_t c = next_chunk.fetch_add(1);
-      if (c >= chunks.size()) return;
-      const Chunk ch = chunks[c];
-      Device &d = ctx->devs[ch.g];
-      const Shard sh = shard_of(n, ch.g, G);
-      b2p_state16 *stage = (b2p_state16 *)d.h_states.ptr + ch.lo;
-      const unsigned char *from = src + kStateBytes * (sh.lo + ch.lo);
-      for (size_t i = 0; i < ch.len; i++) pack_one(from + kStateBytes * i, stage + i);
+      const size_t t = next_task.fetch_add(1);
+      if (t >= tasks.size()) return;
+      const Task tk = tasks[t];
+      Segment &sg = *segs[tk.seg];
+      Device &d = ctx->devs[sg.g];
+      const Shard sh = shard_of(n, sg.g, G);
+      b2p_state16 *stage = (b2p_state16 *)d.h_states.ptr + sg.lo + tk.lo;
+      const unsigned char *from = src + kStateBytes * (sh.lo + sg.lo + tk.lo);
+      for (size_t i = 0; i < tk.len; i++) pack_one(from + kStateBytes * i, stage + i);
+      if (sg.todo.fetch_sub(1) != 1) continue;
+      // last task of the segment: queue its GPU work
       std::lock_guard<std::mutex> lock(enqueue_mu);
-      if (!err.empty()) return;
-      cudaStream_t st = d.aux[c % 4] ? d.aux[c % 4] : d.stream;
+      if (!err.empty()) continue;
+      const unsigned a = d.next_aux++ % 4;
+      cudaStream_t st = d.aux[a] ? d.aux[a] : d.stream;
       cudaError_t e = cudaSetDevice(d.id);
       if (e == cudaSuccess)
-        e = cudaMemcpyAsync((b2p_state16 *)d.d_states.ptr + ch.lo, stage, ch.len * sizeof(b2p_state16), cudaMemcpyHostToDevice, st);
+        e = cudaMemcpyAsync((b2p_state16 *)d.d_states.ptr + sg.lo, (b2p_state16 *)d.h_states.ptr + sg.lo, sg.len * sizeof(b2p_state16),
+                            cudaMemcpyHostToDevice, st);
       if (e == cudaSuccess) {
         PlayoutParams prm;
         std::memset(&prm, 0, sizeof prm);
-        prm.states = reinterpret_cast<const uint4 *>((b2p_state16 *)d.d_states.ptr + ch.lo);
-        prm.n = (uint32_t)ch.len;
-        prm.total = (uint32_t)ch.len;
+        prm.states = reinterpret_cast<const uint4 *>((b2p_state16 *)d.d_states.ptr + sg.lo);
+        prm.n = (uint32_t)sg.len;
+        prm.total = (uint32_t)sg.len;
         prm.rep_stride = n;
         prm.key = key;
-        prm.pid_base = sh.lo + ch.lo;
+        prm.pid_base = sh.lo + sg.lo;
         prm.max_plies = -1;
-        prm.winners = (int8_t *)d.d_winners.ptr + ch.lo;
-        prm.next = next_slot(d);
-        e = use_warp_kernel(sched, n, km) ? launch_playout_warp(prm, km, d.sm_count, st, nullptr)
-                                          : launch_playout_lanes(prm, km, d.sm_count, st, nullptr);
-        ctx->launches++;
+        prm.winners = (int8_t *)d.d_winners.ptr + sg.lo;
+        e = launch_playouts(ctx, d, prm, km, sched, st);  // AUTO decides on the size of THIS launch
       }
       if (e == cudaSuccess)
-        e = cudaMemcpyAsync((int8_t *)d.h_winners.ptr + ch.lo, (int8_t *)d.d_winners.ptr + ch.lo, ch.len, cudaMemcpyDeviceToHost, st);
+        e = cudaMemcpyAsync((int8_t *)d.h_winners.ptr + sg.lo, (int8_t *)d.d_winners.ptr + sg.lo, sg.len, cudaMemcpyDeviceToHost, st);
       if (e != cudaSuccess) err = std::string("b2p_run_states776 pipeline: ") + cudaGetErrorString(e);
     }
   };
-  {
-    const unsigned hw = std::thread::hardware_concurrency();
-    const size_t workers = std::min<size_t>(std::min<size_t>(hw ? hw : 1, 32), chunks.size());
-    std::vector<std::thread> th;
-    for (size_t t = 1; t < workers; t++) th.emplace_back(worker);
-    worker();
-    for (auto &t : th) t.join();
-  }
-  if (!err.empty()) return fail(ctx, B2P_ECUDA, err);
+  ctx->pool.run(tasks.size(), worker);
+  // wait for every stream that may carry work of this call -- also on the error path: the next call may
+  // grow (free + reallocate) buffers that kernels still in flight are writing
+  cudaError_t sync_err = cudaSuccess;
   for (int g = 0; g < G; g++) {
     Device &d = ctx->devs[g];
-    const Shard sh = shard_of(n, g, G);
-    const size_t nl = sh.hi - sh.lo;
-    B2P_CUDA(ctx, cudaSetDevice(d.id));
+    cudaError_t e = cudaSetDevice(d.id);
     for (cudaStream_t a : d.aux)
-      if (a) B2P_CUDA(ctx, cudaStreamSynchronize(a));
-    B2P_CUDA(ctx, cudaStreamSynchronize(d.stream));
-    const int8_t *w = (const int8_t *)d.h_winners.ptr;
-    parallel_for(nl, 1 << 16, [&](size_t lo, size_t hi) {
-      for (size_t i = lo; i < hi; i++) winners_out[sh.lo + i] = (int32_t)w[i];  // PlayerId is a 4-byte enum
-    });
+      if (a && e == cudaSuccess) e = cudaStreamSynchronize(a);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);
+    if (e != cudaSuccess && sync_err == cudaSuccess) sync_err = e;
   }
+  if (!err.empty()) return fail(ctx, B2P_ECUDA, err);
+  if (sync_err != cudaSuccess) return fail(ctx, B2P_ECUDA, std::string("b2p_run_states776: ") + cudaGetErrorString(sync_err));
+  // PlayerId is a 4-byte enum: widen the int8 winners into the caller's array
+  std::atomic<size_t> next_block{0};
+  const size_t kWiden = 1 << 16, blocks = (n + kWiden - 1) / kWiden;
+  auto widen = [&]() {
+    for (;;) {
+      const size_t b = next_block.fetch_add(1);
+      if (b >= blocks) return;
+      const size_t lo = b * kWiden, hi = std::min(n, lo + kWiden);
+      int g = 0;
+      for (size_t i = lo; i < hi;) {
+        while (shard_of(n, g, G).hi <= i) g++;
+        const Shard sh = shard_of(n, g, G);
+        const int8_t *w = (const int8_t *)ctx->devs[g].h_winners.ptr - sh.lo;
+        const size_t stop = std::min(hi, sh.hi);
+        for (; i < stop; i++) winners_out[i] = (int32_t)w[i];
+      }
+    }
+  };
+  ctx->pool.run(blocks, widen);
   return B2P_OK;
 }
 
@@ -632,7 +780,7 @@ int b2p_genmoves(b2p_ctx *ctx, const b2p_state16 *states, size_t n, int max_move
   if (!ctx) return B2P_EINVAL;
   if (n == 0) return B2P_OK;
   if (!states || !moves_out || !counts_out || max_moves <= 0) return fail(ctx, B2P_EINVAL, "bad genmoves arguments");
-  const int G = (int)std::min<size_t>(ctx->devs.size(), n);
+  const int G = device_span(ctx, n, n);
   for (int g = 0; g < G; g++) {
     Device &d = ctx->devs[g];
     const Shard sh = shard_of(n, g, G);
@@ -659,7 +807,7 @@ int b2p_gen_leaves(b2p_ctx *ctx, size_t n, uint64_t key, uint64_t first_index, b
   if (!ctx) return B2P_EINVAL;
   if (n == 0) return B2P_OK;
   if (!out) return fail(ctx, B2P_EINVAL, "out is NULL");
-  const int G = (int)std::min<size_t>(ctx->devs.size(), n);
+  const int G = device_span(ctx, n, n);
   for (int g = 0; g < G; g++) {
     Device &d = ctx->devs[g];
     const Shard sh = shard_of(n, g, G);

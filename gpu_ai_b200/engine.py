@@ -47,6 +47,8 @@ ABI = [
     ("b2p_gen_leaves_device", _INT, [_VP, _INT, _SZ, _U64, _U64, _VP, _VP]),
     ("b2p_gen_leaves", _INT, [_VP, _SZ, _U64, _U64, _VP]),
     ("b2p_sync", _INT, [_VP]),
+    ("b2p_alloc_host", _INT, [C.POINTER(_VP), _SZ]),
+    ("b2p_free_host", _INT, [_VP]),
     ("b2p_pack776", _INT, [_VP, _SZ, _VP]),
     ("b2p_unpack776", _INT, [_VP, _SZ, _VP]),
     ("b2p_expand_move", _INT, [_U64, _VP]),
@@ -160,11 +162,13 @@ class Engine:
         return out
 
     def run_packed(self, states, reps=1, key=12345, pid_base=0, mode=MODE_RANDOM, sched=SCHED_THREAD,
-                   order=ORDER_CANONICAL, max_plies=-1, want_winners=True, want_plies=False, want_final=False):
+                   order=ORDER_CANONICAL, max_plies=-1, want_winners=True, want_plies=False, want_final=False,
+                   winners_out=None):
+        """winners_out: optional preallocated int8[n*reps] (e.g. a PinnedArray's .array) to receive the winners."""
         a = _as_packed(states)
         n = a.shape[0]
         total = n * reps
-        winners = np.empty(total, dtype=np.int8) if want_winners else None
+        winners = (winners_out if winners_out is not None else np.empty(total, dtype=np.int8)) if want_winners else None
         plies = np.empty(total, dtype=np.uint32) if want_plies else None
         final = np.empty((total, 4), dtype=np.uint32) if want_final else None
         counters = np.zeros(4, dtype=np.uint64)
@@ -172,11 +176,12 @@ class Engine:
                                             _ptr(winners), _ptr(plies), _ptr(final), _ptr(counters)))
         return winners, plies, final, counters
 
-    def run_counts(self, states, reps, key=12345, pid_base=0, mode=MODE_RANDOM, sched=SCHED_THREAD, order=ORDER_FAST):
+    def run_counts(self, states, reps, key=12345, pid_base=0, mode=MODE_RANDOM, sched=SCHED_THREAD, order=ORDER_FAST,
+                   wins_out=None):
         """`reps` playouts per leaf; returns (wins[n, 2] uint32, counters[4])."""
         a = _as_packed(states)
         n = a.shape[0]
-        wins = np.zeros((n, 2), dtype=np.uint32)
+        wins = wins_out if wins_out is not None else np.zeros((n, 2), dtype=np.uint32)
         counters = np.zeros(4, dtype=np.uint64)
         self._check(self.lib.b2p_run_counts(self.ctx, _ptr(a), n, reps, key, pid_base, mode, sched, order, _ptr(wins), _ptr(counters)))
         return wins, counters
@@ -280,6 +285,27 @@ class Tree:
         rc = self.lib.b2p_tree_search(engine.ctx, self.h, iterations, seconds, initial_batch, scale, reps, mode, key, C.byref(played))
         self._check(rc)
         return int(played.value)
+
+
+class PinnedArray:
+    """numpy view of a page-locked buffer from b2p_alloc_host (freed when the object dies)."""
+
+    def __init__(self, shape, dtype):
+        self.lib = load_library()
+        self.ptr = C.c_void_p()
+        dt = np.dtype(dtype)
+        nbytes = int(np.prod(shape)) * dt.itemsize
+        rc = self.lib.b2p_alloc_host(C.byref(self.ptr), nbytes)
+        if rc != 0:
+            raise B2PError("b2p_alloc_host failed (%d): %s" % (rc, (self.lib.b2p_last_error(None) or b"").decode()))
+        buf = (C.c_uint8 * nbytes).from_address(self.ptr.value) if nbytes else (C.c_uint8 * 0)()
+        self.array = np.frombuffer(buf, dtype=dt).reshape(shape)
+
+    def __del__(self):
+        if getattr(self, "ptr", None) and self.ptr.value:
+            self.array = None
+            self.lib.b2p_free_host(self.ptr)
+            self.ptr = C.c_void_p()
 
 
 # ---- converters (no context, no device) -------------------------------------------------------------

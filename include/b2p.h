@@ -16,6 +16,10 @@
  *     across calls; the reference mallocs and frees on every call, src/singlePlayout.cu:80-116).
  *   - one context = one caller at a time; different contexts may be used concurrently from
  *     different host threads (MCTSPlayer worker threads, src/player.cpp:119-150).
+ *   - the device-resident calls may be issued on any caller stream and any number of them may be in
+ *     flight: each launch takes a work-queue head from a 256-slot ring whose slots are guarded by events
+ *     (a wrapped slot waits for the launch that used it last).
+ *   - host-buffer calls use a second device only when every shard keeps >= 8192 playouts.
  *   - there is NO CPU execution path: without a usable CUDA device b2p_create fails.
  *
  * Packed state (16 bytes): square i = row*4 + col/2 over the 32 dark squares (the numbering of
@@ -132,6 +136,14 @@ int b2p_gen_leaves_device(b2p_ctx *ctx, int dev_index, size_t n, uint64_t key, u
                           b2p_state16 *d_out, void *cuda_stream);
 int b2p_gen_leaves(b2p_ctx *ctx, size_t n, uint64_t key, uint64_t first_index, b2p_state16 *out);
 int b2p_sync(b2p_ctx *ctx);
+
+/* ---- caller-visible pinned host memory (the zero-copy side of the boundary) ----------------
+ * The reference hands `std::vector<State>` storage (pageable) to cudaMemcpy on every call
+ * (src/singlePlayout.cu:83-91).  Buffers obtained here are page-locked and portable across the context's
+ * devices: b2p_run_packed / b2p_run_counts / b2p_genmoves then copy to and from them with true asynchronous
+ * DMA instead of the driver's pageable staging path.  Any host pointer is still accepted everywhere. */
+int b2p_alloc_host(void **out, size_t bytes);
+int b2p_free_host(void *ptr);
 
 /* ---- layout converters (host, multi-threaded; no device involved) ------------------------------
  * struct State <-> b2p_state16.  type/owner are read only where `occupied` is set: State::move

@@ -308,13 +308,21 @@ def test_run_counts_equals_winner_tally(engine):
         assert np.array_equal(c, c2)
 
 
-# ---- in-process multi-device sharding (needs >= 2 visible GPUs; skipped on a 1-GPU box) --------------------------
-def test_in_process_multi_device_equals_single_device(engine):
+# ---- in-process multi-device sharding (what the shim uses: b2p_create with several devices) ------------------------
+def _multi_device_ids():
+    """All visible GPUs when there are several; on a 1-GPU box the SAME device three times: the context then
+    owns three independent Device records (streams, staging, buffers, queue-head rings), so the sharding,
+    gather-at-offset and host-combine logic runs exactly as it does over distinct GPUs."""
     import torch
+    n = torch.cuda.device_count()
+    return list(range(n)) if n >= 2 else [0, 0, 0]
+
+
+def test_in_process_multi_device_equals_single_device(engine):
     import gpu_ai_b200 as b
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs at least 2 GPUs")
-    multi = b.Engine(devices=torch.cuda.device_count(), seed=12345)
+    ids = _multi_device_ids()
+    multi = b.Engine(devices=ids, seed=12345)
+    assert multi.device_count == len(ids)
     st = np.concatenate([engine.gen_leaves(70001, key=12), fast_synthetic(10000, 29)])
     assert np.array_equal(multi.gen_leaves(70001, key=12), st[:70001])
     for mode, order in ((MODE_RANDOM, ORDER_FAST), (MODE_HEURISTIC, ORDER_CANONICAL)):
@@ -329,12 +337,100 @@ def test_in_process_multi_device_equals_single_device(engine):
     mc, nc = multi.genmoves(st, 40)
     assert np.array_equal(ma, mc) and np.array_equal(na, nc)
     s776 = b.engine.unpack776(st)
-    e1, e2 = b.Engine(devices=1, seed=99), b.Engine(devices=torch.cuda.device_count(), seed=99)
+    e1, e2 = b.Engine(devices=1, seed=99), b.Engine(devices=ids, seed=99)
     assert np.array_equal(e1.run_states776(s776), e2.run_states776(s776))
+    # below the minimum shard (8192 playouts per device) a batch stays on one device: same answers
+    assert np.array_equal(e1.run_states776(s776[:5000]), e2.run_states776(s776[:5000]))
     t1, t2 = b.Tree(START_PACKED), b.Tree(START_PACKED)
-    t1.search(engine, iterations=6, initial_batch=3000, reps=4, key=2)
-    t2.search(multi, iterations=6, initial_batch=3000, reps=4, key=2)
+    t1.search(engine, iterations=6, initial_batch=30000, reps=4, key=2)
+    t2.search(multi, iterations=6, initial_batch=30000, reps=4, key=2)
     assert np.array_equal(t1.root_moves()[1], t2.root_moves()[1]) and np.array_equal(t1.root_moves()[2], t2.root_moves()[2])
+
+
+@pytest.mark.parametrize("n", [1, 50, 511, 512, 513, 2049, 8191, 8193, 10239, 10240, 20000, 40961, 65536, 65537, 131073])
+def test_run_states776_every_batch_size_class(port, n):
+    """Pack tasks (512 states) and launch segments (8192..32768 leaves, short tails merged) at their edges: the
+    reference-facing call returns the replayable winners for every size class of tests.sh."""
+    import gpu_ai_b200 as b
+    eng = b.Engine(devices=_multi_device_ids(), seed=7)
+    st = eng.gen_leaves(n, key=2016, first_index=11)
+    res = eng.run_states776(port.unpack776(st), mode=b.MODE_RANDOM, sched=b.SCHED_THREAD)
+    ow, _, _, _ = port.playouts(st, key=7, order=ORDER_FAST)
+    assert np.array_equal(res, ow.astype(np.int32))
+
+
+def test_many_launches_in_flight_on_caller_streams(engine, port):
+    """More launches than the 256-slot queue-head ring, spread over several caller streams without a
+    synchronisation in between: every launch still sees a zeroed head of its own (event-guarded ring)."""
+    import torch
+    dev = torch.device("cuda", 0)
+    n = 3000
+    st = engine.gen_leaves(n, key=9)
+    d_states = torch.from_numpy(st.view(np.int32)).to(dev)
+    streams = [torch.cuda.Stream(device=dev) for _ in range(4)]
+    outs = [torch.empty(n, dtype=torch.int8, device=dev) for _ in range(600)]
+    torch.cuda.synchronize()
+    for i, o in enumerate(outs):
+        engine.run_packed_device(d_states.data_ptr(), n, key=1000 + (i % 3), order=ORDER_FAST, d_winners=o.data_ptr(),
+                                 stream=streams[i % 4].cuda_stream)
+    torch.cuda.synchronize()
+    expect = [port.playouts(st, key=1000 + k, order=ORDER_FAST)[0] for k in range(3)]
+    for i, o in enumerate(outs):
+        assert np.array_equal(o.cpu().numpy(), expect[i % 3]), "launch %d" % i
+
+
+def test_pinned_host_buffers(engine):
+    import gpu_ai_b200 as b
+    from gpu_ai_b200.engine import PinnedArray
+    st = engine.gen_leaves(50000, key=3)
+    pin_s, pin_w = PinnedArray((50000, 4), np.uint32), PinnedArray((50000,), np.int8)
+    pin_s.array[:] = st
+    w, _, _, c = engine.run_packed(st, key=4, order=ORDER_FAST)
+    w2, _, _, c2 = engine.run_packed(pin_s.array, key=4, order=ORDER_FAST, winners_out=pin_w.array)
+    assert w2 is pin_w.array and np.array_equal(w, w2) and np.array_equal(c, c2)
+    lib = b.load_library()
+    assert lib.b2p_alloc_host(None, 16) == -1 and lib.b2p_free_host(None) == 0
+
+
+# ---- the real drop-in binary: the reference's run_ai linked against shim/playout_shim.cpp + libb2p.so ---------------
+def _run_ai(*args, timeout=600):
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "shim", "_ref", "run_ai_b200")
+    if not os.path.exists(exe):
+        pytest.skip("shim/_ref/run_ai_b200 not built (needs /root/reference in the build container: make -C shim)")
+    r = subprocess.run([exe] + list(args), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=timeout)
+    assert r.returncode == 0, r.stdout[-2000:]
+    return r.stdout
+
+
+def _tallies(text):
+    import re
+    d = [int(x) for x in re.findall(r"Games drawn: (\d+)", text)]
+    a = [int(x) for x in re.findall(r"Player 1 wins: (\d+)", text)]
+    c = [int(x) for x in re.findall(r"Player 2 wins: (\d+)", text)]
+    assert len(d) == 2 and len(a) == 2 and len(c) == 2, text[-1500:]
+    return [(d[i], a[i], c[i]) for i in range(2)]
+
+
+def test_drop_in_binary_gen_moves_test():
+    """`run_ai -m gen_moves_test` (src/driver.cpp:106-117): the reference's own host State::genMoves against
+    the B200 move generator through the shim's genMovesTest, 20000 random states of ITS genRandomStates."""
+    out = _run_ai("-m", "gen_moves_test", "-n", "20000")
+    assert "Passed" in out and "Mismatch" not in out and "Failed" not in out, out[-1500:]
+
+
+@pytest.mark.parametrize("dev,host", [("device_single", "host"), ("device_multiple", "host"), ("device_coarse", "host"),
+                                      ("device_heuristic", "host_heuristic")])
+def test_drop_in_binary_playout_test(dev, host):
+    """`run_ai -m playout_test -n 100000 -1 <device driver> -2 <host driver>` (src/driver.cpp:119-170): both
+    drivers play the same 100000 leaves inside the reference binary; outcome tallies within |z| < 4."""
+    n = 100000
+    (d0, a0, c0), (d1, a1, c1) = _tallies(_run_ai("-m", "playout_test", "-n", str(n), "-1", dev, "-2", host))
+    assert d0 + a0 + c0 == n and d1 + a1 + c1 == n
+    for x, y in ((d0, d1), (a0, a1), (c0, c1)):
+        assert abs(_z(x, n, y, n)) < 4.0, "%s %s vs %s %s" % (dev, (d0, a0, c0), host, (d1, a1, c1))
 
 
 def test_b200_mcts_player_plays_legal_moves(engine, port):
