@@ -24,6 +24,7 @@
 #include <thread>
 #include <vector>
 
+#include "hostpool.h"
 #include "kernels.cuh"
 
 using namespace b2p;
@@ -36,6 +37,13 @@ struct Buffer {
   void *ptr = nullptr;
   size_t cap = 0;
   bool pinned = false;
+};
+
+// one pipeline slot of the asynchronous count call (b2p_run_counts_async): its own device buffers, runs on aux[slot]
+constexpr int kSlots = 4;
+struct Slot {
+  Buffer d_states, d_counts, d_misc, h_misc;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // around the kernel: b2p_wait_slot reports the kernel time
 };
 
 struct Device {
@@ -53,70 +61,9 @@ struct Device {
   std::vector<cudaEvent_t> ring_ev;
   std::vector<char> ring_busy;
   unsigned next_aux = 0;  // round-robin over `aux` per DEVICE (segments of b2p_run_states776)
+  Slot slots[kSlots];
 };
 
-// Persistent host workers of a context (packing 776-byte States, widening results): created on first use,
-// parked on a condition variable between calls.  The reference-facing call used to spawn std::threads per call.
-class Pool {
- public:
-  ~Pool() {
-    {
-      std::lock_guard<std::mutex> l(mu_);
-      stop_ = true;
-    }
-    cv_.notify_all();
-    for (auto &t : th_) t.join();
-  }
-  // runs f() on `workers` threads in total (the caller is one of them); returns when all have returned
-  void run(size_t workers, const std::function<void()> &f) {
-    const unsigned hw = std::thread::hardware_concurrency();
-    const size_t cap = std::min<size_t>(hw ? hw : 1, 32);
-    workers = std::min(workers, cap);
-    if (workers <= 1) {
-      f();
-      return;
-    }
-    const size_t helpers = workers - 1;
-    {
-      std::lock_guard<std::mutex> l(mu_);
-      while (th_.size() < helpers) th_.emplace_back([this, id = th_.size()] { loop(id); });
-      job_ = &f;
-      want_ = helpers;
-      pending_ = helpers;
-      gen_++;
-    }
-    cv_.notify_all();
-    f();
-    std::unique_lock<std::mutex> l(mu_);
-    done_.wait(l, [this] { return pending_ == 0; });
-    job_ = nullptr;
-  }
-
- private:
-  void loop(size_t id) {
-    uint64_t seen = 0;
-    for (;;) {
-      const std::function<void()> *job = nullptr;
-      {
-        std::unique_lock<std::mutex> l(mu_);
-        cv_.wait(l, [&] { return stop_ || (gen_ != seen && id < want_); });
-        if (stop_) return;
-        seen = gen_;
-        job = job_;
-      }
-      (*job)();
-      std::lock_guard<std::mutex> l(mu_);
-      if (--pending_ == 0) done_.notify_one();
-    }
-  }
-  std::vector<std::thread> th_;
-  std::mutex mu_;
-  std::condition_variable cv_, done_;
-  const std::function<void()> *job_ = nullptr;
-  size_t want_ = 0, pending_ = 0;
-  uint64_t gen_ = 0;
-  bool stop_ = false;
-};
 
 }  // namespace
 
@@ -126,7 +73,8 @@ struct b2p_ctx {
   uint64_t calls = 0;
   std::atomic<uint64_t> launches{0};
   std::string err;
-  Pool pool;
+  b2p::Pool pool;
+  int slot_span[kSlots] = {0, 0, 0, 0};  // devices used by the call in flight on each slot (0 = idle)
 };
 
 namespace {
@@ -359,6 +307,11 @@ void b2p_destroy(b2p_ctx *ctx) {
       if (a) cudaStreamSynchronize(a);
     for (cudaEvent_t ev : d.ring_ev)
       if (ev) cudaEventDestroy(ev);
+    for (Slot &sl : d.slots) {
+      for (Buffer *b : {&sl.d_states, &sl.d_counts, &sl.d_misc, &sl.h_misc}) release(*b);
+      if (sl.ev0) cudaEventDestroy(sl.ev0);
+      if (sl.ev1) cudaEventDestroy(sl.ev1);
+    }
     for (Buffer *b : {&d.d_states, &d.d_winners, &d.d_plies, &d.d_final, &d.d_moves, &d.d_counts, &d.d_misc, &d.h_states, &d.h_winners, &d.h_misc}) release(*b);
     if (d.d_next_ring) cudaFree(d.d_next_ring);
     if (d.ev0) cudaEventDestroy(d.ev0);
@@ -641,6 +594,82 @@ int b2p_run_counts(b2p_ctx *ctx, const b2p_state16 *states, size_t n, uint32_t r
     B2P_CUDA(ctx, cudaStreamSynchronize(d.stream));
     if (counters_out)
       for (int k = 0; k < 4; k++) counters_out[k] += ((const uint64_t *)d.h_misc.ptr)[k];
+  }
+  return B2P_OK;
+}
+
+// Asynchronous form of b2p_run_counts for a pipelined caller (b2p_tree_search_ex): queues H2D copy, kernel and D2H
+// copy of the per-leaf counts on pipeline slot `slot` of every device the batch is sharded over and returns at once.
+int b2p_run_counts_async(b2p_ctx *ctx, int slot, const b2p_state16 *states, size_t n, uint32_t reps, uint64_t key,
+                         uint64_t pid_base, int mode, int sched, int order, uint32_t *wins_out) {
+  if (!ctx) return B2P_EINVAL;
+  if (slot < 0 || slot >= kSlots) return fail(ctx, B2P_EINVAL, "bad pipeline slot");
+  if (ctx->slot_span[slot] != 0) return fail(ctx, B2P_EINVAL, "pipeline slot still in flight: call b2p_wait_slot first");
+  if (n == 0 || reps == 0) return B2P_OK;
+  if (!states || !wins_out) return fail(ctx, B2P_EINVAL, "NULL buffer");
+  KernelMode km;
+  if (!mode_to_kernel(mode, order, &km)) return fail(ctx, B2P_EINVAL, "unknown mode/order");
+  const int G = device_span(ctx, n, n * (size_t)reps);
+  for (int g = 0; g < G; g++)
+    if ((unsigned long long)(shard_of(n, g, G).hi - shard_of(n, g, G).lo) * reps >= (1ull << 31))
+      return fail(ctx, B2P_EINVAL, "per-device n*reps must be < 2^31");
+  for (int g = 0; g < G; g++) {
+    Device &d = ctx->devs[g];
+    Slot &sl = d.slots[slot];
+    cudaStream_t st = d.aux[slot] ? d.aux[slot] : d.stream;
+    const Shard sh = shard_of(n, g, G);
+    const size_t nl = sh.hi - sh.lo;
+    B2P_CUDA(ctx, cudaSetDevice(d.id));
+    int rc;
+    if ((rc = ensure(ctx, sl.d_states, nl * sizeof(b2p_state16), false))) return rc;
+    if ((rc = ensure(ctx, sl.d_counts, nl * 2 * sizeof(uint32_t), false))) return rc;
+    if ((rc = ensure(ctx, sl.d_misc, 4 * sizeof(uint64_t), false))) return rc;
+    if ((rc = ensure(ctx, sl.h_misc, 4 * sizeof(uint64_t), true))) return rc;
+    if (!sl.ev0) B2P_CUDA(ctx, cudaEventCreate(&sl.ev0));
+    if (!sl.ev1) B2P_CUDA(ctx, cudaEventCreate(&sl.ev1));
+    B2P_CUDA(ctx, cudaMemcpyAsync(sl.d_states.ptr, states + sh.lo, nl * sizeof(b2p_state16), cudaMemcpyHostToDevice, st));
+    B2P_CUDA(ctx, cudaMemsetAsync(sl.d_misc.ptr, 0, 4 * sizeof(uint64_t), st));
+    B2P_CUDA(ctx, cudaMemsetAsync(sl.d_counts.ptr, 0, nl * 2 * sizeof(uint32_t), st));
+    PlayoutParams prm;
+    std::memset(&prm, 0, sizeof prm);
+    prm.states = reinterpret_cast<const uint4 *>(sl.d_states.ptr);
+    prm.n = (uint32_t)nl;
+    prm.total = (uint32_t)(nl * reps);
+    prm.rep_stride = n;
+    prm.key = key;
+    prm.pid_base = pid_base + sh.lo;
+    prm.max_plies = -1;
+    prm.leaf_wins = (unsigned int *)sl.d_counts.ptr;
+    prm.counters = (unsigned long long *)sl.d_misc.ptr;
+    B2P_CUDA(ctx, cudaEventRecord(sl.ev0, st));
+    const cudaError_t e = launch_playouts(ctx, d, prm, km, sched, st);
+    if (e != cudaSuccess) return fail(ctx, B2P_ECUDA, std::string("playout launch: ") + cudaGetErrorString(e));
+    B2P_CUDA(ctx, cudaEventRecord(sl.ev1, st));
+    B2P_CUDA(ctx, cudaMemcpyAsync(wins_out + 2 * sh.lo, sl.d_counts.ptr, nl * 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    B2P_CUDA(ctx, cudaMemcpyAsync(sl.h_misc.ptr, sl.d_misc.ptr, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    ctx->slot_span[slot] = g + 1;
+  }
+  return B2P_OK;
+}
+
+int b2p_wait_slot(b2p_ctx *ctx, int slot, uint64_t counters_out[4], float *kernel_ms_out) {
+  if (!ctx) return B2P_EINVAL;
+  if (slot < 0 || slot >= kSlots) return fail(ctx, B2P_EINVAL, "bad pipeline slot");
+  if (counters_out) counters_out[0] = counters_out[1] = counters_out[2] = counters_out[3] = 0;
+  if (kernel_ms_out) *kernel_ms_out = 0.f;
+  const int G = ctx->slot_span[slot];
+  ctx->slot_span[slot] = 0;
+  for (int g = 0; g < G; g++) {
+    Device &d = ctx->devs[g];
+    Slot &sl = d.slots[slot];
+    B2P_CUDA(ctx, cudaSetDevice(d.id));
+    B2P_CUDA(ctx, cudaStreamSynchronize(d.aux[slot] ? d.aux[slot] : d.stream));
+    if (counters_out)
+      for (int k = 0; k < 4; k++) counters_out[k] += ((const uint64_t *)sl.h_misc.ptr)[k];
+    if (kernel_ms_out) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, sl.ev0, sl.ev1) == cudaSuccess && ms > *kernel_ms_out) *kernel_ms_out = ms;
+    }
   }
   return B2P_OK;
 }

@@ -41,6 +41,8 @@ ABI = [
     ("b2p_run_states776", _INT, [_VP, _VP, _SZ, _INT, _INT, _VP]),
     ("b2p_run_packed", _INT, [_VP, _VP, _SZ, _U32, _U64, _U64, _INT, _INT, _INT, _INT, _VP, _VP, _VP, _VP]),
     ("b2p_run_counts", _INT, [_VP, _VP, _SZ, _U32, _U64, _U64, _INT, _INT, _INT, _VP, _VP]),
+    ("b2p_run_counts_async", _INT, [_VP, _INT, _VP, _SZ, _U32, _U64, _U64, _INT, _INT, _INT, _VP]),
+    ("b2p_wait_slot", _INT, [_VP, _INT, _VP, C.POINTER(C.c_float)]),
     ("b2p_genmoves", _INT, [_VP, _VP, _SZ, _INT, _VP, _VP]),
     ("b2p_run_packed_device", _INT, [_VP, _INT, _VP, _SZ, _U32, _U64, _U64, _INT, _INT, _INT, _INT, _VP, _VP, _VP, _VP, _VP]),
     ("b2p_genmoves_device", _INT, [_VP, _INT, _VP, _SZ, _INT, _VP, _VP, _VP]),
@@ -65,6 +67,9 @@ ABI = [
     ("b2p_tree_root_moves", _INT, [_VP, _VP, _VP, _VP, _VP, _U32]),
     ("b2p_tree_last_error", C.c_char_p, [_VP]),
     ("b2p_tree_search", _INT, [_VP, _VP, _U32, C.c_double, _U32, C.c_float, _U32, _INT, _U64, C.POINTER(_U64)]),
+    ("b2p_tree_search_ex", _INT, [_VP, _VP, _VP, _VP]),
+    ("b2p_tree_select_batch", _INT, [_VP, _INT, _U32, _U32, _INT, _INT, _VP]),
+    ("b2p_tree_update_batch", _INT, [_VP, _INT, _VP, _INT]),
 ]
 
 _lib = None
@@ -218,6 +223,17 @@ class Engine:
         return ops.value, ms.value
 
 
+class SearchOpts(C.Structure):
+    _fields_ = [("iterations", _U32), ("seconds", C.c_double), ("initial_batch", _U32), ("scale", C.c_float),
+                ("max_batch", _U32), ("reps", _U32), ("mode", _INT), ("key", _U64), ("threads", _INT), ("depth", _INT)]
+
+
+class SearchStats(C.Structure):
+    _fields_ = [("playouts", _U64), ("leaves", _U64), ("batches", _U64), ("nodes", _U64), ("seconds", C.c_double),
+                ("select_s", C.c_double), ("update_s", C.c_double), ("wait_s", C.c_double), ("kernel_s", C.c_double),
+                ("threads", _U32), ("depth", _U32)]
+
+
 class TreeStats(C.Structure):
     _fields_ = [("nodes", _U64), ("total_trials", _U64), ("wins_p1", _U64), ("wins_p2", _U64), ("root_children", _U32),
                 ("root_moves", _U32), ("root_state", _U32 * 4)]
@@ -285,6 +301,23 @@ class Tree:
         rc = self.lib.b2p_tree_search(engine.ctx, self.h, iterations, seconds, initial_batch, scale, reps, mode, key, C.byref(played))
         self._check(rc)
         return int(played.value)
+
+    def select_batch(self, slot, trials, reps=1, threads=1, exact=True):
+        out = np.empty((max(trials, 1), 4), dtype=np.uint32)
+        self._check(self.lib.b2p_tree_select_batch(self.h, slot, trials, reps, threads, int(exact), _ptr(out)))
+        return out[:trials]
+
+    def update_batch(self, slot, wins, threads=1):
+        w = np.ascontiguousarray(wins, dtype=np.uint32)
+        self._check(self.lib.b2p_tree_update_batch(self.h, slot, _ptr(w), threads))
+
+    def search_ex(self, engine, iterations=0, seconds=0.0, initial_batch=50, scale=0.02, max_batch=0, reps=1,
+                  mode=MODE_RANDOM, key=1, threads=0, depth=0):
+        """b2p_tree_search_ex: returns the b2p_search_stats as a dict."""
+        o = SearchOpts(iterations, seconds, initial_batch, scale, max_batch, reps, mode, key, threads, depth)
+        st = SearchStats()
+        self._check(self.lib.b2p_tree_search_ex(engine.ctx, self.h, C.byref(o), C.byref(st)))
+        return {k: getattr(st, k) for k, _ in SearchStats._fields_}
 
 
 class PinnedArray:

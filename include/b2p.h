@@ -115,6 +115,15 @@ int b2p_run_packed(b2p_ctx *ctx, const b2p_state16 *states, size_t n, uint32_t r
 int b2p_run_counts(b2p_ctx *ctx, const b2p_state16 *states, size_t n, uint32_t reps, uint64_t key, uint64_t pid_base,
                    int mode, int sched, int order, uint32_t *wins_out, uint64_t counters_out[4]);
 
+/* Asynchronous, pipelined form of b2p_run_counts (the caller side of SURVEY.md 8f-1/8f-2: select of batch k+1 overlaps
+ * the playouts of batch k).  `slot` in [0, 4): each slot has its own stream and device buffers on every device, so up
+ * to four batches may be in flight.  b2p_run_counts_async queues H2D copy + kernel + D2H copy and returns at once;
+ * `states` and `wins_out` must stay valid (and should be page-locked: b2p_alloc_host) until b2p_wait_slot(slot)
+ * returns.  counters_out / kernel_ms_out may be NULL; kernel_ms = device time of the slot's kernel (max over devices). */
+int b2p_run_counts_async(b2p_ctx *ctx, int slot, const b2p_state16 *states, size_t n, uint32_t reps, uint64_t key,
+                         uint64_t pid_base, int mode, int sched, int order, uint32_t *wins_out);
+int b2p_wait_slot(b2p_ctx *ctx, int slot, uint64_t counters_out[4], float *kernel_ms_out);
+
 /* ---- move generation (replaces genMovesKernel / genMovesTest, src/genMovesTest.cu:10-100) ----
  * moves_out[i*max_moves + k] = k-th move of State::getMoves() for states[i] (k < max_moves);
  * counts_out[i] = number of legal moves (may exceed max_moves). */
@@ -197,6 +206,42 @@ const char *b2p_tree_last_error(const b2p_tree *tree);
  * rounds or `seconds` of wall clock (0 = unlimited on that axis; both 0 = nothing). */
 int b2p_tree_search(b2p_ctx *ctx, b2p_tree *tree, uint32_t iterations, double seconds, uint32_t initial_batch,
                     float scale, uint32_t reps, int mode, uint64_t key, uint64_t *playouts_out);
+
+/* The same loop with its knobs and its accounting exposed.  The loop is a pipeline: leaf selection runs on
+ * `threads` host threads (disjoint subtrees), batches travel through page-locked staging to b2p_run_counts_async,
+ * and with depth >= 2 the selection + statistics update of one batch overlap the playouts of the previous one
+ * (in-flight trials count as visits without wins).  depth == 1 is the strictly serial loop: it takes exactly the
+ * decisions of b2p_tree_select -> b2p_run_counts -> b2p_tree_update_counts, for any `threads` and any number of
+ * devices.  Results are deterministic for given options (the time limit only decides how many rounds run). */
+typedef struct b2p_search_opts {
+  uint32_t iterations;    /* rounds; 0 = until `seconds` */
+  double seconds;         /* wall-clock budget; 0 = until `iterations` */
+  uint32_t initial_batch; /* leaves per round, lower bound */
+  float scale;            /* leaves per round = max(initial_batch, scale * leaf selections so far) ... */
+  uint32_t max_batch;     /* ... capped here (0 = 2^20) and by 2^31 / reps */
+  uint32_t reps;          /* playouts per selected leaf */
+  int mode;               /* B2P_MODE_* */
+  uint64_t key;           /* Philox key of round r = key + r; playout ids count up over the whole search */
+  int threads;            /* host threads for select/update; 0 = min(hardware threads, 16) */
+  int depth;              /* batches in flight: 1 serial, 2..4 pipelined; 0 = 2 */
+} b2p_search_opts;
+typedef struct b2p_search_stats {
+  uint64_t playouts, leaves, batches, nodes;
+  double seconds;                     /* wall clock of the whole call */
+  double select_s, update_s, wait_s;  /* host time: selecting, updating, blocked on the GPU */
+  double kernel_s;                    /* device time of the playout kernels (max over devices per batch) */
+  uint32_t threads, depth;
+} b2p_search_stats;
+/* The two host halves of one pipelined round, for a caller that runs the playouts itself.  select_batch picks
+ * `trials` leaves on `threads` host threads (same decisions as b2p_tree_select), counts them into the visited nodes
+ * as `reps` trials each and remembers the batch in `slot` (0..3); exact != 0 evaluates UCB1 with the reference's
+ * expression types (bit-identical decisions, what depth 1 uses), 0 in single precision (what depth >= 2 uses:
+ * a quarter of the cycles); update_batch folds the batch's per-leaf win counts
+ * (b2p_run_counts layout) into the nodes it visited.  Several slots may be selected before the first is updated. */
+int b2p_tree_select_batch(b2p_tree *tree, int slot, uint32_t trials, uint32_t reps, int threads, int exact,
+                          b2p_state16 *leaves_out);
+int b2p_tree_update_batch(b2p_tree *tree, int slot, const uint32_t *wins, int threads);
+int b2p_tree_search_ex(b2p_ctx *ctx, b2p_tree *tree, const b2p_search_opts *opts, b2p_search_stats *stats_out);
 
 #ifdef __cplusplus
 }

@@ -151,3 +151,67 @@ def test_tree_equals_reference_gametree_random_roots(ref, golden):
         for x, y in zip(a, c):
             assert x.shape == y.shape and np.array_equal(x, y)
         assert mine.info()["total_trials"] == theirs.total()
+
+
+# ---- the pipelined search's host halves (b2p_tree_select_batch / b2p_tree_update_batch), no GPU needed -------------
+def fake_counts(leaves, reps, salt):
+    w = np.stack([fake_winners(leaves, salt + 1000 * r) for r in range(reps)])
+    return np.stack([(w == 0).sum(axis=0), (w == 1).sum(axis=0)], axis=1).astype(np.uint32)
+
+
+@pytest.mark.parametrize("threads", [1, 3, 8])
+def test_batch_pipeline_depth1_equals_serial_interface(threads):
+    """One batch in flight = the strictly serial loop: the parallel, record-based select/update makes exactly the
+    decisions of b2p_tree_select / b2p_tree_update_counts (and therefore of the reference GameTree), for any
+    number of host threads -- same leaves in the same order, same statistics."""
+    import gpu_ai_b200 as b
+    reps = 3
+    for root in (START_PACKED, make_state(p1_kings=[(2, 1)], p1_men=[(1, 4)], p2_men=[(5, 2), (6, 5)], p2_kings=[(7, 0)])):
+        a, c = b.Tree(root), b.Tree(root)
+        for it, n in enumerate([50, 1, 2, 7, 300, 5000, 64, 20000, 3, 9000]):
+            la = a.select(n)
+            lc = c.select_batch(it % 4, n, reps=reps, threads=threads)
+            assert np.array_equal(la, lc), "batch %d" % it
+            wins = fake_counts(la, reps, 7 * it)
+            a.update_counts(wins, reps)
+            c.update_batch(it % 4, wins, threads=threads)
+            ia, ic = a.info(), c.info()
+            assert ia["total_trials"] == ic["total_trials"] and ia["wins"] == ic["wins"] and ia["nodes"] == ic["nodes"]
+            for x, y in zip(a.root_moves(), c.root_moves()):
+                assert np.array_equal(x, y)
+            if it == 5:
+                m = a.best_move(int(root[3] & 1))
+                assert m == c.best_move(int(root[3] & 1))
+                a.move(m)
+                c.move(m)
+
+
+def test_batch_pipeline_two_in_flight_is_consistent_and_deterministic():
+    """Two batches selected before the first is updated (virtual loss): every playout is accounted for exactly
+    once, wins never exceed trials anywhere the root can see, and the result does not depend on the thread count."""
+    import gpu_ai_b200 as b
+    reps = 4
+    runs = []
+    for threads in (1, 6):
+        t = b.Tree(START_PACKED)
+        sizes = [4000, 4000, 6000, 100, 12000, 12000, 50]
+        pending = []
+        total = 0
+        for it, n in enumerate(sizes):
+            leaves = t.select_batch(it % 2, n, reps=reps, threads=threads)
+            assert len(leaves) == n
+            total += n * reps
+            assert t.info()["total_trials"] == total          # in-flight trials are visible as visits at once
+            pending.append((it % 2, fake_counts(leaves, reps, it), leaves.copy()))
+            if len(pending) == 2:
+                slot, wins, _ = pending.pop(0)
+                t.update_batch(slot, wins, threads=threads)
+        for slot, wins, _ in pending:
+            t.update_batch(slot, wins, threads=threads)
+        info = t.info()
+        mv, tr, w1, w2 = t.root_moves()
+        assert tr.sum() == total and info["wins"][0] == w1.sum() and info["wins"][1] == w2.sum()
+        assert ((w1 + w2) <= tr).all()
+        runs.append((tr.copy(), w1.copy(), w2.copy(), info["nodes"]))
+    for x, y in zip(runs[0], runs[1]):
+        assert np.array_equal(x, y)

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
-"""Host throughput of the tree operations: b2p_tree vs the reference's GameTree (when oracle/_ref is present).
-select + update with free (fake) playout results, so only the caller-side cost is measured (SURVEY.md 6:
-the reference sustains ~3e5 leaves/s)."""
+"""Host-side throughput of the search tree (no GPU): leaf selections/s of b2p_tree_select_batch + b2p_tree_update_batch
+(the two host halves of a pipelined search round) and of the serial interface, from the initial position, with fake
+playout results.  Usage: tree_bench.py [threads ...]"""
 import json
 import os
 import sys
@@ -9,35 +9,36 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import gpu_ai_b200 as b  # noqa: E402
-from oracle import pyoracle  # noqa: E402
-from test_tree import RefTree, fake_winners  # noqa: E402
 
-
-def run(tree, batches):
-    t_sel = t_upd = 0.0
-    n_leaves = 0
-    for i, n in enumerate(batches):
-        t0 = time.perf_counter()
-        leaves = tree.select(n)
-        t1 = time.perf_counter()
-        w = fake_winners(leaves, i)
-        t2 = time.perf_counter()
-        tree.update(w)
-        t3 = time.perf_counter()
-        t_sel += t1 - t0
-        t_upd += t3 - t2
-        n_leaves += len(leaves)
-    return {"leaves": n_leaves, "select_leaves_per_s": n_leaves / t_sel, "update_leaves_per_s": n_leaves / t_upd,
-            "select_plus_update_leaves_per_s": n_leaves / (t_sel + t_upd)}
-
-
-batches = [50] + [4000] * 60
-out = {"b2p_tree": run(b.Tree(pyoracle.START_PACKED), batches)}
-if pyoracle.have_reference():
-    out["reference_GameTree"] = run(RefTree(pyoracle.Checker("reference"), pyoracle.START_PACKED), batches)
-    out["cores"] = os.cpu_count()
-print(json.dumps(out, indent=1))
+START = np.array([0x00000FFF, 0xFFF00000, 0, 0], dtype=np.uint32)
+threads_list = [int(x) for x in sys.argv[1:]] or [1, 4, os.cpu_count() or 1]
+rng = np.random.default_rng(1)
+for batch in (4096, 65536, 1 << 20):
+    wins_pool = rng.integers(0, 5, size=(batch, 2)).astype(np.uint32)
+    rounds = max(4, min(200, (1 << 23) // batch))
+    t = b.Tree(START)
+    t0 = time.perf_counter()
+    sel = upd = 0.0
+    for it in range(rounds):
+        a = time.perf_counter()
+        t.select(batch)
+        c = time.perf_counter()
+        t.update_counts(wins_pool, 8)
+        sel += c - a
+        upd += time.perf_counter() - c
+    print(json.dumps({"interface": "serial b2p_tree_select/update_counts", "batch": batch, "rounds": rounds,
+                      "leaves_per_s": batch * rounds / (sel + upd), "select_s": sel, "update_s": upd, "nodes": t.info()["nodes"]}), flush=True)
+    for th, exact in [(x, e) for x in threads_list for e in (True, False)]:
+        t = b.Tree(START)
+        sel = upd = 0.0
+        for it in range(rounds):
+            a = time.perf_counter()
+            t.select_batch(0, batch, reps=8, threads=th, exact=exact)
+            c = time.perf_counter()
+            t.update_batch(0, wins_pool, threads=th)
+            sel += c - a
+            upd += time.perf_counter() - c
+        print(json.dumps({"interface": "b2p_tree_select_batch/update_batch", "threads": th, "exact": exact, "batch": batch, "rounds": rounds,
+                          "leaves_per_s": batch * rounds / (sel + upd), "select_s": sel, "update_s": upd, "nodes": t.info()["nodes"]}), flush=True)
