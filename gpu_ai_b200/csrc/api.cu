@@ -75,6 +75,7 @@ struct b2p_ctx {
   std::string err;
   b2p::Pool pool;
   int slot_span[kSlots] = {0, 0, 0, 0};  // devices used by the call in flight on each slot (0 = idle)
+  Buffer slot_leaves[kSlots], slot_wins[kSlots];  // page-locked staging lent to pipelined callers (b2p_slot_staging)
 };
 
 namespace {
@@ -299,6 +300,10 @@ int b2p_create(b2p_ctx **out, const int *device_ids, int n_dev, uint64_t seed) {
 
 void b2p_destroy(b2p_ctx *ctx) {
   if (!ctx) return;
+  for (int sl = 0; sl < kSlots; sl++) {
+    release(ctx->slot_leaves[sl]);
+    release(ctx->slot_wins[sl]);
+  }
   for (Device &d : ctx->devs) {
     if (d.id < 0) continue;
     cudaSetDevice(d.id);
@@ -649,6 +654,28 @@ int b2p_run_counts_async(b2p_ctx *ctx, int slot, const b2p_state16 *states, size
     B2P_CUDA(ctx, cudaMemcpyAsync(sl.h_misc.ptr, sl.d_misc.ptr, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     ctx->slot_span[slot] = g + 1;
   }
+  return B2P_OK;
+}
+
+// Context-owned page-locked staging for a pipelined caller: room for `leaves` packed states and 2*`leaves` win
+// counts on `slot`.  Grow-only and kept for the life of the context, so a caller that creates many short-lived
+// trees (a tournament, a benchmark) pays for page-locking once.  The slot must be idle.
+int b2p_slot_staging(b2p_ctx *ctx, int slot, size_t leaves, b2p_state16 **leaves_out, uint32_t **wins_out) {
+  if (!ctx) return B2P_EINVAL;
+  if (slot < 0 || slot >= kSlots || !leaves_out || !wins_out) return fail(ctx, B2P_EINVAL, "bad staging arguments");
+  if (ctx->slot_span[slot] != 0) return fail(ctx, B2P_EINVAL, "pipeline slot still in flight: call b2p_wait_slot first");
+  int rc;
+  if ((rc = ensure(ctx, ctx->slot_leaves[slot], leaves * sizeof(b2p_state16), true))) return rc;
+  if ((rc = ensure(ctx, ctx->slot_wins[slot], leaves * 2 * sizeof(uint32_t), true))) return rc;
+  // the slot's device buffers too: growing them later means cudaFree, which synchronises the whole device
+  for (Device &d : ctx->devs) {
+    Slot &sl = d.slots[slot];
+    B2P_CUDA(ctx, cudaSetDevice(d.id));
+    if ((rc = ensure(ctx, sl.d_states, leaves * sizeof(b2p_state16), false))) return rc;
+    if ((rc = ensure(ctx, sl.d_counts, leaves * 2 * sizeof(uint32_t), false))) return rc;
+  }
+  *leaves_out = (b2p_state16 *)ctx->slot_leaves[slot].ptr;
+  *wins_out = (uint32_t *)ctx->slot_wins[slot].ptr;
   return B2P_OK;
 }
 

@@ -277,27 +277,14 @@ struct b2p_tree {
   uint32_t epoch = 0;
   std::string err;
   bool out_of_memory = false;
-  // pipelined search state (grow-only, page-locked through b2p_alloc_host)
+  // pipelined search state; the page-locked leaf / count staging belongs to the context (b2p_slot_staging)
   b2p_state16 *h_leaves[kPipeSlots] = {nullptr, nullptr, nullptr, nullptr};
   uint32_t *h_wins[kPipeSlots] = {nullptr, nullptr, nullptr, nullptr};
-  size_t h_cap = 0;
   std::vector<uint32_t> pre1, pre2;  // prefix sums of the per-leaf win counts (update scratch)
   Batch batch[kPipeSlots];
   Pool pool;
 
-  ~b2p_tree() {
-    release_staging();
-    delete arena;
-  }
-  void release_staging() {
-    for (int s = 0; s < kPipeSlots; s++) {
-      b2p_free_host(h_leaves[s]);
-      b2p_free_host(h_wins[s]);
-      h_leaves[s] = nullptr;
-      h_wins[s] = nullptr;
-    }
-    h_cap = 0;
-  }
+  ~b2p_tree() { delete arena; }
 
   Node &at(uint32_t id) const { return arena->at(id); }
   uint64_t node_count() const {
@@ -626,19 +613,6 @@ struct b2p_tree {
       nd.wins[1] += base2[hi] - base2[lo];
     }
   }
-
-  int ensure_staging(size_t leaves, int slots) {
-    if (leaves <= h_cap && h_leaves[slots - 1]) return B2P_OK;
-    leaves = std::max(leaves, h_cap);
-    release_staging();
-    for (int s = 0; s < slots; s++) {
-      int rc;
-      if ((rc = b2p_alloc_host((void **)&h_leaves[s], leaves * sizeof(b2p_state16))) != B2P_OK) return rc;
-      if ((rc = b2p_alloc_host((void **)&h_wins[s], leaves * 2 * sizeof(uint32_t))) != B2P_OK) return rc;
-    }
-    h_cap = leaves;
-    return B2P_OK;
-  }
 };
 
 extern "C" {
@@ -832,6 +806,17 @@ int b2p_tree_search_ex(b2p_ctx *ctx, b2p_tree *t, const b2p_search_opts *o, b2p_
   uint64_t selected = 0;   // leaf selections so far (finished or in flight)
   int rc = B2P_OK;
   uint32_t launched = 0, retired = 0;
+  // page-locked staging for every slot, sized once for the largest batch this search can reach
+  {
+    uint64_t reach = o->initial_batch;
+    if (o->scale > 0) reach = cap;  // the batch grows with the tree
+    reach = std::min<uint64_t>(std::max<uint64_t>(reach, 1u << 12), cap);
+    for (int s = 0; s < depth; s++)
+      if ((rc = b2p_slot_staging(ctx, s, reach, &t->h_leaves[s], &t->h_wins[s])) != B2P_OK) {
+        t->err = std::string("b2p_tree_search: ") + b2p_last_error(ctx);
+        return rc;
+      }
+  }
 
   auto retire = [&]() -> int {  // wait for the oldest batch in flight and fold its results into the tree
     const int slot = (int)(retired % (uint32_t)depth);
@@ -860,15 +845,6 @@ int b2p_tree_search_ex(b2p_ctx *ctx, b2p_tree *t, const b2p_search_opts *o, b2p_
     uint64_t want = (uint64_t)((double)selected * o->scale);
     if (want < o->initial_batch) want = o->initial_batch;
     const uint32_t n = (uint32_t)std::min<uint64_t>(want, cap);
-    if (n > t->h_cap || !t->h_leaves[depth - 1]) {
-      // growing the page-locked staging frees the old buffers: nothing may be in flight
-      while (retired < launched && rc == B2P_OK) rc = retire();
-      if (rc != B2P_OK) break;
-      if ((rc = t->ensure_staging(std::min<uint64_t>(cap, std::max<uint64_t>(2ull * n, 1u << 16)), depth)) != B2P_OK) {
-        t->err = "b2p_tree_search: pinned staging allocation failed";
-        break;
-      }
-    }
     if (launched - retired == (uint32_t)depth && (rc = retire()) != B2P_OK) break;
     const int slot = (int)(launched % (uint32_t)depth);
     Batch &b = t->batch[slot];

@@ -43,6 +43,7 @@ ABI = [
     ("b2p_run_counts", _INT, [_VP, _VP, _SZ, _U32, _U64, _U64, _INT, _INT, _INT, _VP, _VP]),
     ("b2p_run_counts_async", _INT, [_VP, _INT, _VP, _SZ, _U32, _U64, _U64, _INT, _INT, _INT, _VP]),
     ("b2p_wait_slot", _INT, [_VP, _INT, _VP, C.POINTER(C.c_float)]),
+    ("b2p_slot_staging", _INT, [_VP, _INT, _SZ, C.POINTER(_VP), C.POINTER(_VP)]),
     ("b2p_genmoves", _INT, [_VP, _VP, _SZ, _INT, _VP, _VP]),
     ("b2p_run_packed_device", _INT, [_VP, _INT, _VP, _SZ, _U32, _U64, _U64, _INT, _INT, _INT, _INT, _VP, _VP, _VP, _VP, _VP]),
     ("b2p_genmoves_device", _INT, [_VP, _INT, _VP, _SZ, _INT, _VP, _VP, _VP]),

@@ -123,6 +123,9 @@ int b2p_run_counts(b2p_ctx *ctx, const b2p_state16 *states, size_t n, uint32_t r
 int b2p_run_counts_async(b2p_ctx *ctx, int slot, const b2p_state16 *states, size_t n, uint32_t reps, uint64_t key,
                          uint64_t pid_base, int mode, int sched, int order, uint32_t *wins_out);
 int b2p_wait_slot(b2p_ctx *ctx, int slot, uint64_t counters_out[4], float *kernel_ms_out);
+/* context-owned page-locked staging for `slot`: room for `leaves` states and 2*leaves counts; grow-only, kept for the
+ * life of the context (callers that build many short-lived trees pay for page-locking once); the slot must be idle */
+int b2p_slot_staging(b2p_ctx *ctx, int slot, size_t leaves, b2p_state16 **leaves_out, uint32_t **wins_out);
 
 /* ---- move generation (replaces genMovesKernel / genMovesTest, src/genMovesTest.cu:10-100) ----
  * moves_out[i*max_moves + k] = k-th move of State::getMoves() for states[i] (k < max_moves);
