@@ -657,7 +657,7 @@ def main():
 
     # ---- CPU baseline on this box's host cores (rank 0, N = 1 only) --------------------------------------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sets_for_cpu["ref"] = d_states[: 1 << 17].cpu().numpy().view(np.uint32)
+        sets_for_cpu["ref"] = d_states.cpu().numpy().view(np.uint32)
         if args.no_extras or mode != b.MODE_RANDOM or args.leaf_set != "ref":
             base, _, _ = cpu_playouts_per_s(sets_for_cpu["ref"], args.mode)
         else:

@@ -62,7 +62,7 @@ __device__ __forceinline__ void fill_gauss_table(float2 *tab) {
 // thread-per-playout, persistent lanes
 // ---------------------------------------------------------------------------------------------
 #ifndef B2P_HEUR_MIN_BLOCKS
-#define B2P_HEUR_MIN_BLOCKS 1  // register caps tried (6/7/8 blocks): within +-1 %, profiles/r01i_ab.txt
+#define B2P_HEUR_MIN_BLOCKS 7  // 72 registers, 7 blocks/SM: +5 % over uncapped (99 regs), 8 blocks spills and loses 8 % (profiles/r02g_ab.txt)
 #endif
 #ifndef B2P_RAND_MIN_BLOCKS
 #define B2P_RAND_MIN_BLOCKS 1

@@ -340,10 +340,18 @@ B2P_HD int random_ply(Game &g, uint32_t r) {
 // (i>>1)&3 of noise block i>>3 (philox.cuh): 8 candidates per Philox call.
 // NoiseBlock: Philox4 block(int b);  Gauss: float gauss(uint32_t h16).
 //
-// The common case -- only direct moves, none of them crowning (all candidates share one base
-// weight) -- never identifies the individual moves: it scans the noise stream block by block
-// (one Philox call per 4 candidates, the same blocks at the same time in every lane of a warp),
-// keeps the first maximum of base + noise, and only then maps the winning index to a move.
+// Three kinds of ply, cheapest first:
+//  SCAN  no capture (3 plies in 4).  All non-crowning candidates share ONE base weight, so the winner among
+//        them is the candidate with the largest noise DRAW: gauss() is strictly increasing in the 16-bit draw
+//        (steps of >= 4.2e-6 per unit, tests/test_host_logic.py) and float addition is monotone; a base weight is
+//        at most 48 (eleven kings and a crowning man against one man), so every sum lies below 64 where one ulp
+//        is 3.8e-6: distinct draws give distinct sums.  The scan is therefore an INTEGER
+//        max over keys (draw << 8 | 255 - index): no table look-up, no float work per candidate; the table is
+//        read once for the winner and once per crowning candidate (a handful per game).
+//  LOOP  a capture ply with two or more sequences, all single hops or forced chains (shape 0 / 1): a plain loop
+//        over the few candidates in list order, weight and noise in float exactly as the reference spells it.
+//        (A ply with ONE list entry -- most capture plies -- weighs nothing: the move is forced.)
+//  DFS   a capture ply with a choice after the first hop (shape 2, ~1 % of plies): register DFS.
 struct HeurBest {
   float w;
   int idx;
@@ -351,11 +359,49 @@ struct HeurBest {
 
 B2P_HD bool heur_better(float w, int idx, const HeurBest &b) { return w > b.w || (w == b.w && idx < b.idx); }
 
-// Staged for SIMT: every lane of the calling group walks through the same four stages, and the group is
-// explicitly rejoined (B2P_REJOIN) before the two expensive converged stages.  Without the rejoin points
-// ptxas keeps lanes that took different rare paths apart and runs the noise scan and the index -> move
-// mapping once per sub-group (measured: 1.8 executions per ply).  `lanes` = mask of the lanes that call this
-// function together (device; ignored on the host).  No early return before the last rejoin point.
+B2P_HD uint32_t noise_half(const Philox4 &b, int q) {  // 16-bit draw of candidate q (0..7) of a noise block
+  uint32_t r = b.v[0];
+  r = (q >> 1) == 1 ? b.v[1] : r;
+  r = (q >> 1) == 2 ? b.v[2] : r;
+  r = (q >> 1) == 3 ? b.v[3] : r;
+  return (q & 1) ? r >> 16 : r & 0xFFFFu;
+}
+
+// slots (directions, reference order) of the four candidate masks present at origin o, as a 4-bit value
+B2P_HD uint32_t slots_at(const uint32_t a[4], int o) {
+  return ((a[0] >> o) & 1u) | (((a[1] >> o) & 1u) << 1) | (((a[2] >> o) & 1u) << 2) | (((a[3] >> o) & 1u) << 3);
+}
+
+// A capture that starts with hop (o --d--> land) on a shape-0/1 ply: follows the forced continuation, if any
+// (men: up to two more hops, never a choice; kings: one forced second hop), accumulating the jumped squares.
+B2P_HD void follow_forced_chain(const JumpMasks &jm, bool man, int shape, int &land, uint32_t &cap) {
+  if (shape != 1) return;
+  if (!man) {
+    const uint32_t nib = ((jm.j[0] >> land) & 1u) | (((jm.j[1] >> land) & 1u) << 1) | (((jm.j[2] >> land) & 1u) << 2) |
+                         (((jm.j[3] >> land) & 1u) << 3);
+    if (nib) {
+      const int d2 = lowbit(nib);
+      cap |= 1u << step_target(land, d2);
+      land = jump_target(land, d2);
+    }
+  } else {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int hop = 0; hop < 2; hop++) {  // a man makes at most 3 hops
+      if (!(((jm.j[0] | jm.j[1]) >> land) & 1u)) break;
+      const int d2 = (int)((jm.j[1] >> land) & 1u);  // 1 = UL, 0 = UR (exactly one is available)
+      cap |= 1u << step_target(land, d2);
+      land = jump_target(land, d2);
+    }
+  }
+}
+
+// Staged for SIMT: every lane of the calling group walks through the same stages, and the group is
+// explicitly rejoined (B2P_REJOIN) before the converged ones.  Without the rejoin points ptxas keeps lanes
+// that took different rare paths apart and runs the scan and the index -> move mapping once per sub-group.
+// `lanes` = mask of the lanes that call this function together (device; ignored on the host).  No early
+// return before the last rejoin point.
 // Ratio: float ratio(uint32_t a, uint32_t b) = the correctly rounded IEEE quotient float(a) / float(b)
 // (getWeight, src/heuristic.cu:44-49); the kernels serve it from a shared-memory table of all material pairs.
 template <class NoiseBlock, class Gauss, class Ratio>
@@ -377,41 +423,29 @@ B2P_HD int heuristic_ply(Game &g, unsigned lanes, NoiseBlock &&noise_block, Gaus
   a[2] = m.capture ? m.cap[2] : (ownK & m.e[2]);
   a[3] = m.capture ? m.cap[3] : (ownK & m.e[3]);
   const int n = popc(a[0]) + popc(a[1]) + popc(a[2]) + popc(a[3]);
-  const bool enumerate = !drawn && shape != 0;        // some capture continues: sequences must be enumerated
-  const int n_scan = (drawn || enumerate) ? 0 : n;    // candidates handled by the converged scan
+  const bool dfs = !drawn && shape == 2;
+  // with one list entry there is nothing to weigh: the move is forced (most capture plies)
+  // ... and when the opponent has no piece left every weight is my / 0 = +inf: the first list entry wins
+  const bool choice = !drawn && !dfs && n > 1 && his != 0u;
+  const bool loop = choice && m.capture;
+  const int n_scan = (choice && !loop) ? n : 0;  // candidates handled by the converged integer scan
   uint32_t from = 0, to = 0, captured = 0;
   HeurBest best;
   best.w = -__builtin_inff();
-  best.idx = 0x7fffffff;
+  best.idx = 0;  // no choice: list entry 0
 
-  // Weight classes.  Direct moves: plain / crowning.  Single-hop captures: (man | king captured) x
-  // (plain | crowning).  All candidates of a class share one weight, so the scan only needs to know, per
-  // canonical index, which class a candidate is in: two 64-bit index masks.
-  const uint32_t lo_den = m.capture ? his - 1u : his;
-  const uint32_t hi_den = his >= 4u ? his - 4u : his;  // only used when a king can be captured (his >= 4 then)
-  float w0 = ratio(my, lo_den), w1 = ratio(my + 3u, lo_den);
-  float w2 = ratio(my, hi_den), w3 = ratio(my + 3u, hi_den);
-  B2P_PIN_FLOAT(w0);
-  B2P_PIN_FLOAT(w1);
-  B2P_PIN_FLOAT(w2);
-  B2P_PIN_FLOAT(w3);
-  uint64_t crown_idx = 0, kingcap_idx = 0;
+  // noise block 0 serves candidates 0..7 -- all there are on most plies
+  const Philox4 blk0 = noise_block(0);
 
-  // ---- stage 1 (divergent, short): the rare work --------------------------------------------------------
-  if (enumerate) {
-    // multi-hop sequences: one register-DFS pass buffers the sequences, then they are scored in list order
-    int cached = -1;
-    Philox4 nb;
-    nb.v[0] = nb.v[1] = nb.v[2] = nb.v[3] = 0;
+  // ---- stage 1 (divergent, rare): capture plies with a choice -----------------------------------------------
+  if (dfs) {
+    // ~1 % of plies: one register-DFS pass buffers the sequences, then they are scored in list order
+    int cached = 0;
+    Philox4 nb = blk0;
     auto noise = [&](int idx) {
-      const int blk = idx >> 3;
-      if (blk != cached) { nb = noise_block(blk); cached = blk; }
-      const int q = (idx >> 1) & 3;
-      uint32_t r = nb.v[0];
-      r = q == 1 ? nb.v[1] : r;
-      r = q == 2 ? nb.v[2] : r;
-      r = q == 3 ? nb.v[3] : r;
-      return gauss((idx & 1) ? r >> 16 : r & 0xFFFFu);
+      const int b = idx >> 3;
+      if (b != cached) { nb = noise_block(b); cached = b; }
+      return gauss(noise_half(nb, idx & 7));
     };
     constexpr int kLeafBuf = 12;
     uint32_t buf_captured[kLeafBuf];
@@ -441,74 +475,107 @@ B2P_HD int heuristic_ply(Game &g, unsigned lanes, NoiseBlock &&noise_block, Gaus
         return false;
       });
     }
-  } else if (n_scan > 0) {
-    // class masks: a short loop over the FEW exceptional origins (crowning men for direct moves, the
-    // capturing pieces for captures)
-    uint32_t special = m.capture ? (a[0] | a[1] | a[2] | a[3]) : ((a[0] | a[1]) & ownMen & 0x0F000000u);
-    for (; special; special &= special - 1) {
-      const int o = lowbit(special);
-      const uint32_t below = (1u << o) - 1u;
-      int i = popc(a[0] & below) + popc(a[1] & below) + popc(a[2] & below) + popc(a[3] & below);
+  } else if (loop) {
+    // a few % of plies: two or more captures (single hops or forced chains).  ONE loop body per candidate, walked in list order by peeling (origin, slot) pairs: every lane in
+    // here runs the same instructions, only the trip count differs.  Scores only; the move is built in stage 3.
+    uint32_t origins = a[0] | a[1] | a[2] | a[3];
+    int o = lowbit(origins);
+    uint32_t nib = slots_at(a, o);
+    Philox4 nb = blk0;
+    int cached = 0;
+    for (int k = 0; k < n; k++) {
+      const int slot = lowbit(nib);
       const bool man = (ownMen >> o) & 1u;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-      for (int slot = 0; slot < 4; slot++) {
-        if (!((a[slot] >> o) & 1u)) continue;
-        const int d = (m.capture && man) ? (slot ^ 1) : slot;
-        const int mid = step_target(o, d);
-        const int land = m.capture ? jump_target(o, d) : mid;
-        const int idx = rev ? n - 1 - i : i;
-        if (man && land >= 28) crown_idx |= 1ull << idx;
-        if (m.capture && ((p.kings >> mid) & 1u)) kingcap_idx |= 1ull << idx;
-        i++;
+      const int d = (m.capture && man) ? (slot ^ 1) : slot;
+      const int mid = step_target(o, d);
+      int land = m.capture ? jump_target(o, d) : mid;
+      uint32_t cap = m.capture ? (1u << mid) : 0u;
+      follow_forced_chain(m.jm, man, shape, land, cap);
+      const int idx = rev ? n - 1 - k : k;
+      const uint32_t promo = (man && land >= 28) ? 3u : 0u;
+      const uint32_t loss = (uint32_t)(popc(cap) + 3 * popc(cap & p.kings));
+      if ((idx >> 3) != cached) { cached = idx >> 3; nb = noise_block(cached); }  // more than 8 candidates: rare
+      const float w = ratio(my + promo, his - loss) + gauss(noise_half(nb, idx & 7));
+      if (heur_better(w, idx, best)) { best.w = w; best.idx = idx; }
+      // next (origin, slot) pair
+      nib &= nib - 1;
+      if (nib == 0u) {
+        origins &= origins - 1;
+        o = origins ? lowbit(origins) : 0;
+        nib = slots_at(a, o);
       }
     }
   }
 
-  // ---- stage 2 (converged): scan the noise stream (8 candidates per Philox block) ------------------------
+  // ---- stage 2 (converged): direct-move plies, integer scan of the noise draws ---------------------------
   B2P_REJOIN(lanes);
-  // half a Philox block (4 candidates) per trip: a lane with 9 candidates costs 3 trips, not 2 x 8
-  Philox4 blk;
-  blk.v[0] = blk.v[1] = blk.v[2] = blk.v[3] = 0;
-  for (int hb = 0; 4 * hb < n_scan; hb++) {
-    const bool upper = hb & 1;
-    if (!upper) blk = noise_block(hb >> 1);
-    const uint32_t word_a = upper ? blk.v[2] : blk.v[0], word_b = upper ? blk.v[3] : blk.v[1];
-    const uint32_t crown4 = (uint32_t)(crown_idx >> (4 * hb)) & 0xFu, kc4 = (uint32_t)(kingcap_idx >> (4 * hb)) & 0xFu;
+  {
+    // crowning candidates (men stepping onto the last row) carry another base weight: a second integer maximum
+    uint64_t crown_idx = 0;
+    if (n_scan > 0) {
+      for (uint32_t special = (a[0] | a[1]) & ownMen & 0x0F000000u; special; special &= special - 1) {
+        const int o = lowbit(special);
+        const uint32_t below = (1u << o) - 1u;
+        const int i = popc(a[0] & below) + popc(a[1] & below) + popc(a[2] & below) + popc(a[3] & below);
+        const int cnt = (int)((a[0] >> o) & 1u) + (int)((a[1] >> o) & 1u);  // a man has slots 0 and 1 only
+        crown_idx |= (uint64_t)(cnt == 2 ? 3u : 1u) << i;                   // normalised positions i (, i + 1)
+      }
+      if (rev) {
+        // canonical index = n - 1 - normalised index: reverse the low n bits
+        const uint64_t r = ((uint64_t)brev((uint32_t)crown_idx) << 32) | (uint64_t)brev((uint32_t)(crown_idx >> 32));
+        crown_idx = r >> (64 - n_scan);
+      }
+    }
+    const uint64_t all = n_scan >= 64 ? ~0ull : ((1ull << n_scan) - 1ull);
+    const uint64_t plain = all & ~crown_idx;
+    uint32_t key0 = 0, key1 = 0;
+    for (int b = 0; 8 * b < n_scan; b++) {
+      const Philox4 blk = b == 0 ? blk0 : noise_block(b);
+      const uint32_t plain8 = (uint32_t)(plain >> (8 * b)) & 0xFFu, crown8 = (uint32_t)(crown_idx >> (8 * b)) & 0xFFu;
+      const uint32_t tail = 255u - 8u * (uint32_t)b;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (int q = 0; q < 4; q++) {
-      const int idx = 4 * hb + q;
-      const uint32_t word = (q & 2) ? word_b : word_a;
-      const uint32_t h = (q & 1) ? word >> 16 : word & 0xFFFFu;
-      const bool crown = (crown4 >> q) & 1u, kc = (kc4 >> q) & 1u;
-      const float base = kc ? (crown ? w3 : w2) : (crown ? w1 : w0);
-      const float w = base + gauss(h);
-      if (idx < n_scan && w > best.w) { best.w = w; best.idx = idx; }
+      for (int q = 0; q < 8; q++) {
+        const uint32_t word = blk.v[q >> 1];
+        const uint32_t h8 = (q & 1) ? ((word >> 8) & 0xFFFF00u) : ((word << 8) & 0xFFFF00u);
+        const uint32_t key = h8 | (tail - (uint32_t)q);
+        const uint32_t c0 = ((plain8 >> q) & 1u) ? key : 0u, c1 = ((crown8 >> q) & 1u) ? key : 0u;
+        key0 = c0 > key0 ? c0 : key0;
+        key1 = c1 > key1 ? c1 : key1;
+      }
+    }
+    if (n_scan > 0) {
+      // two float evaluations settle the ply: the best plain and the best crowning candidate
+      const float s0 = key0 ? ratio(my, his) + gauss(key0 >> 8) : -__builtin_inff();
+      const float s1 = key1 ? ratio(my + 3u, his) + gauss(key1 >> 8) : -__builtin_inff();
+      const int i0 = 255 - (int)(key0 & 0xFFu), i1 = 255 - (int)(key1 & 0xFFu);
+      const bool take1 = s1 > s0 || (s1 == s0 && i1 < i0);
+      best.idx = take1 ? i1 : i0;
     }
   }
 
-  // ---- stage 3 (converged): winning index -> move -------------------------------------------------------
+  // ---- stage 3 (converged): winning list position -> move --------------------------------------------------
   B2P_REJOIN(lanes);
-  {
-    const int pick = n_scan > 0 ? (rev ? n - 1 - best.idx : best.idx) : 0;
-    const int sel = select_origin_major(a, pick);
+  if (!dfs) {
+    const int pick = rev ? n - 1 - best.idx : best.idx;
+    const int sel = select_origin_major(a, n > 0 ? pick : 0);
     const int o = sel & 31;
-    int d = sel >> 5;
-    if (m.capture && ((ownMen >> o) & 1u)) d ^= 1;
-    const int mid = step_target(o, d);
-    if (n_scan > 0) {
-      from = 1u << o;
-      to = 1u << ((m.capture ? jump_target(o, d) : mid) & 31);
-      captured = m.capture ? (1u << (mid & 31)) : 0u;
-    }
+    const int slot = (sel >> 5) & 3;
+    const bool man = (ownMen >> o) & 1u;
+    const int d = (m.capture && man) ? (slot ^ 1) : slot;
+    const int mid = step_target(o, d) & 31;
+    int land = m.capture ? (jump_target(o, d) & 31) : mid;
+    uint32_t cap = m.capture ? (1u << mid) : 0u;
+    follow_forced_chain(m.jm, man, shape, land, cap);
+    from = 1u << o;
+    to = 1u << (land & 31);
+    captured = cap;
   }
 
   // ---- stage 4: outcome ---------------------------------------------------------------------------------
   if (drawn) return -1;
-  if (!enumerate && n == 0) return (int)(g.turn ^ 1u);
+  if (n == 0) return (int)(g.turn ^ 1u);
   finish_ply(g, m.capture, from, to, captured);
   return kRunning;
 }

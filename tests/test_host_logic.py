@@ -93,3 +93,16 @@ def test_two_level_select_experiment_matches(hostbuild):
     f = hostbuild.lib.hb_select_mismatches
     f.restype = C.c_uint64
     assert f(C.c_uint64(7), C.c_uint64(200000)) == 0
+
+
+def test_integer_noise_scan_premises(port):
+    """heuristic_ply's SCAN path replaces 'first maximum of base + gauss(draw)' by 'maximum draw, lowest index'.
+    That is exact iff (1) gauss() is strictly increasing in the 16-bit draw and (2) its smallest step is larger
+    than one ulp of any sum the scan sees (base weights are at most 48 = eleven kings and a crowning man against
+    one man, noise below 0.39 => sums below 64, where one ulp is 2^-18)."""
+    g = np.array([port.gauss(h) for h in range(0, 65536)], dtype=np.float32)
+    step = np.diff(g.astype(np.float64))
+    assert (step > 0).all()
+    ulp_max = float(np.spacing(np.float32(63.9)))
+    assert ulp_max == 2.0 ** -18 and step.min() > 4.2e-6 and step.min() > 1.1 * ulp_max
+    assert abs(g).max() < 0.39
