@@ -1,19 +1,30 @@
-// shim/match_main.cpp -- BASELINE config 5, literally: the reference's own `mcts_host` player (getPlayer("mcts_host"):
-// MCTSPlayer(50, 0, 7 s, HostPlayoutDriver), src/player.cpp:164-166, pondering on the host cores in its worker
-// thread) against a Player that searches with b2p_tree_search on the B200s.  Built against the UNMODIFIED reference
-// sources (shim/Makefile, build container only); the game loop below is ours, written against the reference's
-// Player interface (src/player.hpp:20-30).
+// shim/match_main.cpp -- BASELINE config 5: game-play tournaments against the reference's own `mcts_host` player.
 //
-//   match_b200 <games> <b200 seconds per move> [batch] [reps]
+//   match_b200 <mode> <games> <seconds A> <seconds B (whole seconds)> [batch] [reps]
+//
+//   mode b200    side A = a Player that searches with b2p_tree_search_ex on the B200s (<seconds A> per move, fractional)
+//   mode hybrid  side A = the reference's `mcts_hybrid` preset (MCTSPlayer(50, 0.02, T, HybridPlayoutDriver(1.2)),
+//                src/player.cpp:173-175) running on the drop-in (shim/playout_shim.cpp + shim/hybrid_b200.cpp)
+//   mode device  side A = the reference's `mcts_device_multiple` preset (MCTSPlayer(50, 0.02, T, DeviceMultiple...))
+//   side B is always the reference's `mcts_host` preset (MCTSPlayer(50, 0, T, HostPlayoutDriver), src/player.cpp:164-166).
+// The presets' 7-second move time (an `unsigned` number of seconds slept in getMove, src/player.cpp:99) is replaced
+// by the command-line budgets; everything else -- tree, pondering worker thread, playout drivers -- is the
+// reference's own object code (built against the UNMODIFIED sources by shim/Makefile).  Colours alternate.
+// One JSON line per game (winner, plies, playouts per move of BOTH sides: the reference players report their tree
+// size through their verbose output, src/player.cpp:101-107) and a summary line.
 #include "player.hpp"   // reference
+#include "playout.hpp"  // reference
 #include "state.hpp"    // reference
 
 #include <chrono>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
 #include <memory>
+#include <sstream>
 #include <stdexcept>
+#include <string>
 
 #include "../include/b2p.h"
 
@@ -40,15 +51,23 @@ class B200TreePlayer : public Player {
   void start() { reset(); }
   Move getMove(const State &state, bool) {
     (void)state;
-    uint64_t played = 0;
-    if (b2p_tree_search(ctx, tree, 0, seconds, batch, 0.02f, reps, B2P_MODE_RANDOM, key++, &played) != B2P_OK)
-      throw std::runtime_error(b2p_tree_last_error(tree));
-    playouts += played;
+    b2p_search_opts o;
+    std::memset(&o, 0, sizeof o);
+    o.seconds = seconds;
+    o.initial_batch = batch;
+    o.scale = 0.02f;
+    o.max_batch = 1u << 18;
+    o.reps = reps;
+    o.mode = B2P_MODE_RANDOM;
+    o.key = key++;
+    b2p_search_stats st;
+    if (b2p_tree_search_ex(ctx, tree, &o, &st) != B2P_OK) throw std::runtime_error(b2p_tree_last_error(tree));
+    playouts += st.playouts;
     moves++;
-    b2p_tree_stats st;
-    b2p_tree_info(tree, &st);
+    b2p_tree_stats ts;
+    b2p_tree_info(tree, &ts);
     b2p_move_t best;
-    if (b2p_tree_best_move(tree, (int)(st.root_state.meta & 1u), &best) != B2P_OK) throw std::runtime_error("no best move");
+    if (b2p_tree_best_move(tree, (int)(ts.root_state.meta & 1u), &best) != B2P_OK) throw std::runtime_error("no best move");
     Move m;
     b2p_expand_move(best, &m);
     return m;
@@ -73,40 +92,83 @@ class B200TreePlayer : public Player {
   b2p_tree *tree = nullptr;
 };
 
+// a reference MCTSPlayer asked for its move with verbose = true: "Tree size: N" is its trial count at that moment
+Move verbose_move(Player &p, const State &s, uint64_t &tree_size_sum, uint64_t &count) {
+  std::ostringstream cap;
+  std::streambuf *old = std::cout.rdbuf(cap.rdbuf());
+  Move m;
+  try {
+    m = p.getMove(s, true);
+  } catch (...) {
+    std::cout.rdbuf(old);
+    throw;
+  }
+  std::cout.rdbuf(old);
+  const std::string text = cap.str();
+  const size_t at = text.find("Tree size: ");
+  if (at != std::string::npos) {
+    tree_size_sum += std::strtoull(text.c_str() + at + 11, nullptr, 10);
+    count++;
+  }
+  return m;
+}
+
 }  // namespace
 
 int main(int argc, char **argv) {
-  const int games = argc > 1 ? std::atoi(argv[1]) : 2;
-  const double seconds = argc > 2 ? std::atof(argv[2]) : 1.0;
-  const uint32_t batch = argc > 3 ? (uint32_t)std::atoi(argv[3]) : 8192, reps = argc > 4 ? (uint32_t)std::atoi(argv[4]) : 32;
-  int score[3] = {0, 0, 0};  // b200 wins, mcts_host wins, draws
+  const std::string mode = argc > 1 ? argv[1] : "b200";
+  const int games = argc > 2 ? std::atoi(argv[2]) : 2;
+  const double seconds_a = argc > 3 ? std::atof(argv[3]) : 1.0;
+  const unsigned seconds_b = argc > 4 ? (unsigned)std::atoi(argv[4]) : 1u;
+  const uint32_t batch = argc > 5 ? (uint32_t)std::atoi(argv[5]) : 16384, reps = argc > 6 ? (uint32_t)std::atoi(argv[6]) : 16;
+  int score[3] = {0, 0, 0};  // A wins, mcts_host wins, draws
+  const char *name_a = mode == "b200" ? "b200_tree" : mode == "hybrid" ? "mcts_hybrid(drop-in)" : "mcts_device_multiple(drop-in)";
   for (int g = 0; g < games; g++) {
-    B200TreePlayer *mine = new B200TreePlayer(seconds, batch, reps);
+    B200TreePlayer *mine = nullptr;
     std::unique_ptr<Player> players[NUM_PLAYERS];
-    const int my_seat = g % 2;  // colours alternate
-    players[my_seat] = std::unique_ptr<Player>(mine);
-    players[1 - my_seat] = getPlayer("mcts_host");
+    const int seat_a = g % 2;  // colours alternate
+    if (mode == "b200") {
+      mine = new B200TreePlayer(seconds_a, batch, reps);
+      players[seat_a] = std::unique_ptr<Player>(mine);
+    } else if (mode == "hybrid") {
+      players[seat_a] = std::make_unique<MCTSPlayer>(50, 0.02f, (unsigned)seconds_a, std::make_unique<HybridPlayoutDriver>(1.2f));
+    } else {
+      players[seat_a] = std::make_unique<MCTSPlayer>(50, 0.02f, (unsigned)seconds_a, std::make_unique<DeviceMultiplePlayoutDriver>());
+    }
+    players[1 - seat_a] = std::make_unique<MCTSPlayer>(50, 0.0f, seconds_b, std::make_unique<HostPlayoutDriver>());
     State state = getStartingState();
     for (auto &p : players) p->start();
     int plies = 0;
+    uint64_t tree_a = 0, moves_a = 0, tree_b = 0, moves_b = 0;
     const auto t0 = std::chrono::steady_clock::now();
     while (!state.isGameOver()) {
-      Move m = players[state.turn]->getMove(state, false);
+      const int seat = (int)state.turn;
+      Move m;
+      if (seat == seat_a && mine) m = players[seat]->getMove(state, false);
+      else if (seat == seat_a) m = verbose_move(*players[seat], state, tree_a, moves_a);
+      else m = verbose_move(*players[seat], state, tree_b, moves_b);
       for (auto &p : players) p->move(m);
       state.move(m);
       plies++;
     }
     const PlayerId winner = state.getWinner();
     const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    const char *who = winner == PLAYER_NONE ? "draw" : ((int)winner == my_seat ? "b200_tree" : "mcts_host");
-    score[winner == PLAYER_NONE ? 2 : ((int)winner == my_seat ? 0 : 1)]++;
-    std::cout << "{\"game\": " << g << ", \"b200_seat\": \"P" << my_seat + 1 << "\", \"winner\": \"" << who << "\", \"plies\": " << plies
-              << ", \"seconds\": " << secs << ", \"b200_playouts_per_move\": " << (mine->moves ? mine->playouts / mine->moves : 0) << "}"
-              << std::endl;
+    const char *who = winner == PLAYER_NONE ? "draw" : ((int)winner == seat_a ? name_a : "mcts_host");
+    score[winner == PLAYER_NONE ? 2 : ((int)winner == seat_a ? 0 : 1)]++;
+    const uint64_t a_per_move = mine ? (mine->moves ? mine->playouts / mine->moves : 0) : (moves_a ? tree_a / moves_a : 0);
+    std::cout << "{\"game\": " << g << ", \"a\": \"" << name_a << "\", \"a_seat\": \"P" << seat_a + 1 << "\", \"winner\": \"" << who
+              << "\", \"plies\": " << plies << ", \"seconds\": " << secs << ", \"a_playouts_per_move\": " << a_per_move
+              << ", \"a_metric\": \"" << (mine ? "playouts run by the move's search" : "tree size (trials) when the move was made, pondering included")
+              << "\", \"mcts_host_tree_size_per_move\": " << (moves_b ? tree_b / moves_b : 0) << "}" << std::endl;
     for (auto &p : players) p->stop();
   }
-  std::cout << "{\"summary\": {\"b200_tree\": " << score[0] << ", \"mcts_host\": " << score[1] << ", \"draw\": " << score[2]
-            << "}, \"b200_seconds_per_move\": " << seconds << ", \"mcts_host\": \"reference preset: 50 playouts per batch, 7 s per move, pondering\"}"
-            << std::endl;
+  // Wilson 95 % interval of A's score rate (draw = half a win)
+  const double n = games, w = score[0] + 0.5 * score[2], z = 1.96;
+  const double ph = n > 0 ? w / n : 0, den = 1 + z * z / n, centre = (ph + z * z / (2 * n)) / den,
+               half = z * std::sqrt(ph * (1 - ph) / n + z * z / (4 * n * n)) / den;
+  std::cout << "{\"summary\": {\"a\": \"" << name_a << "\", \"a_wins\": " << score[0] << ", \"mcts_host_wins\": " << score[1] << ", \"draws\": " << score[2]
+            << ", \"games\": " << games << ", \"a_score_rate\": " << ph << ", \"wilson95\": [" << centre - half << ", " << centre + half << "]}"
+            << ", \"a_seconds_per_move\": " << seconds_a << ", \"mcts_host_seconds_per_move\": " << seconds_b
+            << ", \"mcts_host\": \"reference preset MCTSPlayer(50, 0, T, HostPlayoutDriver), pondering on all host cores\"}" << std::endl;
   return 0;
 }

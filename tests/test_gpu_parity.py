@@ -137,20 +137,35 @@ def _z(count_a, n_a, count_b, n_b):
 
 
 @pytest.mark.parametrize("tag,mode", [("host", MODE_RANDOM), ("host_heuristic", MODE_HEURISTIC)])
-def test_winrates_match_reference_host_driver(engine, golden, tag, mode):
-    """Two-proportion z-test on draws / P1 wins / P2 wins: GPU (Philox) vs the reference's
-    HostPlayoutDriver / HostHeuristicPlayoutDriver (glibc rand / std::normal_distribution) on the same
-    65536 D_ref leaves.  Tolerance: |z| < 4 on each outcome (two-sided p ~ 6e-5 per test)."""
-    ref_tally = golden["ref_%s_tally_65536" % tag]
-    st = engine.gen_leaves(65536, key=2016)
-    reps = 16
-    _, _, _, c = engine.run_packed(st, reps=reps, key=424242, mode=mode, order=ORDER_CANONICAL if mode else ORDER_FAST,
-                                   want_winners=False)
-    n_gpu, n_ref = 65536 * reps, 65536
-    assert int(c[0] + c[1] + c[2]) == n_gpu
-    for k in range(3):
-        z = _z(int(c[k]), n_gpu, int(ref_tally[k]), n_ref)
-        assert abs(z) < 4.0, "outcome %d: gpu %.4f vs reference %.4f (z = %.2f)" % (k, c[k] / n_gpu, ref_tally[k] / n_ref, z)
+def test_winrates_match_reference_host_driver(engine, tag, mode):
+    """Two-proportion z-test on draws / P1 wins / P2 wins: GPU (Philox; heuristic: table Gaussian) against the
+    reference's HostPlayoutDriver / HostHeuristicPlayoutDriver (glibc rand / std::normal_distribution) on the same
+    2^20 D_ref leaves -- >= 10^6 playouts on BOTH sides, overall and per piece-count stratum of the
+    leaf (0-5, 6-9, 10-14, 15-24 pieces).  Tolerance: |z| < 4 on each outcome: +-0.25 % absolute on the whole
+    set (two-sided p ~ 6e-5 per test, 15 tests per mode)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_tallies.npz"))
+    n = int(g["n"])
+    ref_tally = g["ref_%s_tally" % tag]
+    st = engine.gen_leaves(n, key=int(g["leaf_key"]))
+    assert np.uint64(st.astype(np.uint64).sum()) == g["leaves_checksum"]
+    edges = g["strata_edges"]
+    pieces = np.unpackbits((st[:, 0] | st[:, 1]).astype(np.uint32).view(np.uint8)).reshape(n, 32).sum(axis=1)
+    strata = np.digitize(pieces, edges[1:-1])
+    reps = 4
+    w, _, _, c = engine.run_packed(st, reps=reps, key=424242, mode=mode, order=ORDER_CANONICAL if mode else ORDER_FAST)
+    w = w.reshape(reps, n)
+    assert int(c[0] + c[1] + c[2]) == n * reps
+    for s in list(range(len(edges) - 1)) + [-1]:
+        sel = slice(None) if s == -1 else (strata == s)
+        n_ref = int(ref_tally[s].sum())
+        n_gpu = int(n_ref * reps)
+        assert n_ref == (n if s == -1 else int(sel.sum()))
+        for k, v in enumerate((-1, 0, 1)):
+            cnt = int((w[:, sel] == v).sum())
+            z = _z(cnt, n_gpu, int(ref_tally[s][k]), n_ref)
+            assert abs(z) < 4.0, "stratum %d outcome %d: gpu %.4f vs reference %.4f (z = %.2f, n_ref = %d)" % (
+                s, v, cnt / n_gpu, ref_tally[s][k] / n_ref, z, n_ref)
 
 
 # ---- size-independent properties at the full benchmark size ------------------------------------------------
@@ -400,7 +415,8 @@ def _run_ai(*args, timeout=600):
     exe = os.path.join(root, "shim", "_ref", "run_ai_b200")
     if not os.path.exists(exe):
         pytest.skip("shim/_ref/run_ai_b200 not built (needs /root/reference in the build container: make -C shim)")
-    r = subprocess.run([exe] + list(args), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=timeout)
+    r = subprocess.run([exe] + list(args), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=timeout,
+                       env=dict(os.environ, B2P_ROUTING_REPORT="1"))
     assert r.returncode == 0, r.stdout[-2000:]
     return r.stdout
 
@@ -414,6 +430,14 @@ def _tallies(text):
     return [(d[i], a[i], c[i]) for i in range(2)]
 
 
+def test_drop_in_binary_hybrid_routes_tiny_batches_to_the_host():
+    """below the device's launch-latency floor (a handful of playouts) the re-tuned hybrid driver plays on the host"""
+    import json
+    out = _run_ai("-m", "playout_test", "-n", "1", "-1", "hybrid", "-2", "hybrid")
+    rep = [json.loads(line) for line in out.splitlines() if line.startswith('{"b2p_routing"')]
+    assert rep and rep[0]["calls_host"] >= 1 and rep[0]["calls_host"] + rep[0]["calls_device"] == 2, rep
+
+
 def test_drop_in_binary_gen_moves_test():
     """`run_ai -m gen_moves_test` (src/driver.cpp:106-117): the reference's own host State::genMoves against
     the B200 move generator through the shim's genMovesTest, 20000 random states of ITS genRandomStates."""
@@ -422,12 +446,20 @@ def test_drop_in_binary_gen_moves_test():
 
 
 @pytest.mark.parametrize("dev,host", [("device_single", "host"), ("device_multiple", "host"), ("device_coarse", "host"),
-                                      ("device_heuristic", "host_heuristic")])
+                                      ("device_heuristic", "host_heuristic"), ("hybrid", "host"), ("optimal", "host"),
+                                      ("optimal_heuristic", "host_heuristic")])
 def test_drop_in_binary_playout_test(dev, host):
     """`run_ai -m playout_test -n 100000 -1 <device driver> -2 <host driver>` (src/driver.cpp:119-170): both
     drivers play the same 100000 leaves inside the reference binary; outcome tallies within |z| < 4."""
     n = 100000
-    (d0, a0, c0), (d1, a1, c1) = _tallies(_run_ai("-m", "playout_test", "-n", str(n), "-1", dev, "-2", host))
+    out = _run_ai("-m", "playout_test", "-n", str(n), "-1", dev, "-2", host)
+    (d0, a0, c0), (d1, a1, c1) = _tallies(out)
+    if dev in ("hybrid", "optimal_heuristic"):
+        # the B200 re-tuning of HybridPlayoutDriver / OptimalHeuristicPlayoutDriver (shim/hybrid_b200.cpp): a batch
+        # of this size goes whole to the device
+        import json
+        rep = [json.loads(line) for line in out.splitlines() if line.startswith('{"b2p_routing"')]
+        assert rep and rep[0]["playouts_device"] == n and rep[0]["playouts_host"] == 0, rep
     assert d0 + a0 + c0 == n and d1 + a1 + c1 == n
     for x, y in ((d0, d1), (a0, a1), (c0, c1)):
         assert abs(_z(x, n, y, n)) < 4.0, "%s %s vs %s %s" % (dev, (d0, a0, c0), host, (d1, a1, c1))

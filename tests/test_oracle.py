@@ -3,6 +3,8 @@
 Three anchors: (1) golden vectors produced by the unmodified reference (tools/make_golden.py),
 (2) the live reference build oracle/_ref when present, (3) published known answers: the perft
 table of SURVEY.md 8c and the Random123 Philox4x32-10 known-answer vectors."""
+import os
+
 import numpy as np
 import pytest
 
@@ -115,3 +117,27 @@ def test_port_equals_live_reference_playouts(port, ref, mode, order):
 
 def test_live_reference_perft_10(ref):
     assert ref.perft(START_PACKED, 10) == PERFT[9]
+
+
+def test_gaussian_noise_substitute_is_gaussian(port):
+    """The heuristic noise is N(0, 0.11^2) in the reference (std::normal_distribution, src/heuristicPlayout.cpp:15-16,
+    src/heuristic.hpp:5-8); here it is a 1025-entry quantile table read with a uniform 16-bit draw.  Independent
+    check of that table -- one generated artefact shared by oracle and product -- against the analytic law:
+    Kolmogorov distance of the draw -> value map to Phi(x / 0.11), moments, symmetry, clipping point."""
+    import re
+    from scipy.stats import norm
+    g = np.array([port.gauss(h) for h in range(65536)], dtype=np.float64)   # every draw is equally likely
+    assert (np.diff(g) > 0).all()
+    # value of draw h is the (h + 1/2) / 65536 quantile: sup |F_table - F_normal| over all atoms
+    u = (np.arange(65536) + 0.5) / 65536.0
+    ks = np.abs(norm.cdf(g / 0.11) - u).max()
+    assert ks < 5e-4, ks
+    assert abs(g.mean()) < 2e-5 and abs(g.std() / 0.11 - 1.0) < 5e-3
+    assert abs(np.mean((g / 0.11) ** 4) - 3.0) < 0.05                        # kurtosis of a Gaussian
+    assert np.abs(g[1:] + g[1:][::-1]).max() < 2e-6                           # symmetric: draw h mirrors draw 65536 - h
+    assert 3.3 < g.max() / 0.11 < 3.6                                        # clipped near +-3.49 sigma
+    # the product ships the same bits
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    bits = [re.findall(r"0x[0-9a-fA-F]{8}", open(os.path.join(here, d, "gauss_table_bits.h")).read())
+            for d in ("oracle", os.path.join("gpu_ai_b200", "csrc"))]
+    assert bits[0] == bits[1] and len(bits[0]) == 1025
