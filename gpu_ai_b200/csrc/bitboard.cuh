@@ -127,6 +127,26 @@ B2P_HD int jump_target(int s, int d) {
   return s + (int)(int8_t)base;
 }
 
+// the same as single-bit MASK arithmetic: the square one step / one jump away from the single-bit mask `from` in
+// direction d is a rotation of the word by the table amount (minus one on odd rows for a step); the caller
+// guarantees that the target is on the board, so nothing wraps.  One funnel shift instead of
+// bit index -> arithmetic -> 1 << index.
+B2P_HD uint32_t rotl32(uint32_t x, uint32_t amt) {
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_l(x, x, amt);
+#else
+  amt &= 31u;
+  return amt ? (x << amt) | (x >> (32u - amt)) : x;
+#endif
+}
+B2P_HD uint32_t step_mask(uint32_t from, int d) {
+  const uint32_t odd = (from & kOddRows) ? 1u : 0u;
+  return rotl32(from, ((0x1C1D0405u >> (8 * d)) & 0xFFu) - odd);  // +5, +4, -3, -4 (mod 32), one less on odd rows
+}
+B2P_HD uint32_t jump_mask(uint32_t from, int d) {
+  return rotl32(from, (0x17190709u >> (8 * d)) & 0xFFu);          // +9, +7, -7, -9 (mod 32)
+}
+
 // ---- position in the mover-normalised frame -----------------------------------------------
 struct Pos {
   uint32_t own;    // pieces of the side to move
@@ -217,6 +237,17 @@ B2P_HD int select_bit(uint32_t m, int k) {
 //                                    order in the normalised frame
 // Returns origin | slot << 5 for rank k (0 <= k < total).
 enum { kOrderCanonical = 0, kOrderFast = 1 };
+
+// direction-major rank k as (single-bit origin mask, slot): no bit index is ever formed
+B2P_HD uint32_t select_dir_major_mask(const uint32_t a[4], int n0, int n1, int n2, int k, int &slot) {
+  slot = 0;
+  uint32_t m = a[0];
+  if (k >= n0) { k -= n0; m = a[1]; slot = 1;
+    if (k >= n1) { k -= n1; m = a[2]; slot = 2;
+      if (k >= n2) { k -= n2; m = a[3]; slot = 3; } } }
+  for (; k > 0; k--) m &= m - 1;
+  return m & (0u - m);
+}
 
 B2P_HD int select_dir_major(const uint32_t a[4], int n0, int n1, int n2, int k) {
   int slot = 0;

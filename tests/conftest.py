@@ -43,9 +43,12 @@ class HostBuild(pyoracle.Checker):
         so = os.path.join(d, "libb2p_hosttest.so")
         srcs = [os.path.join(d, "hostlib.cpp")] + [os.path.join(ROOT, "gpu_ai_b200", "csrc", f)
                                                    for f in ("bitboard.cuh", "philox.cuh", "playout_core.cuh")]
-        if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
+        defs = os.environ.get("B2P_HOST_DEFS", "").split()   # experiment flags (e.g. -DB2P_MASK_TARGETS): same tests
+        if defs:
+            so = os.path.join(d, "libb2p_hosttest_exp.so")
+        if defs or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
             subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-fopenmp", "-ffp-contract=off", "-shared", "-o", so,
-                            srcs[0]], check=True)
+                            srcs[0]] + defs, check=True)
         self.kind = "hostbuild"
         self.lib = C.CDLL(so)
         self.pfx = "hb_"
