@@ -1,6 +1,6 @@
 // shim/match_main.cpp -- BASELINE config 5: game-play tournaments against the reference's own `mcts_host` player.
 //
-//   match_b200 <mode> <games> <seconds A> <seconds B (whole seconds)> [batch] [reps]
+//   match_b200 <mode> <games> <seconds A> <seconds B (whole seconds)> [batch] [reps] [scale]
 //
 //   mode b200    side A = a Player that searches with b2p_tree_search_ex on the B200s (<seconds A> per move, fractional)
 //   mode hybrid  side A = the reference's `mcts_hybrid` preset (MCTSPlayer(50, 0.02, T, HybridPlayoutDriver(1.2)),
@@ -39,7 +39,7 @@ b2p_move_t encode(const Move &m) {
 
 class B200TreePlayer : public Player {
  public:
-  B200TreePlayer(double seconds, uint32_t batch, uint32_t reps) : seconds(seconds), batch(batch), reps(reps) {
+  B200TreePlayer(double seconds, uint32_t batch, uint32_t reps, float scale) : seconds(seconds), batch(batch), reps(reps), scale(scale) {
     if (b2p_create(&ctx, nullptr, 0, 12345) != B2P_OK) throw std::runtime_error(b2p_last_error(nullptr));
     reset();
   }
@@ -55,7 +55,7 @@ class B200TreePlayer : public Player {
     std::memset(&o, 0, sizeof o);
     o.seconds = seconds;
     o.initial_batch = batch;
-    o.scale = 0.02f;
+    o.scale = scale;
     o.max_batch = 1u << 18;
     o.reps = reps;
     o.mode = B2P_MODE_RANDOM;
@@ -87,6 +87,7 @@ class B200TreePlayer : public Player {
   }
   double seconds;
   uint32_t batch, reps;
+  float scale;
   uint64_t key = 1;
   b2p_ctx *ctx = nullptr;
   b2p_tree *tree = nullptr;
@@ -120,7 +121,10 @@ int main(int argc, char **argv) {
   const int games = argc > 2 ? std::atoi(argv[2]) : 2;
   const double seconds_a = argc > 3 ? std::atof(argv[3]) : 1.0;
   const unsigned seconds_b = argc > 4 ? (unsigned)std::atoi(argv[4]) : 1u;
-  const uint32_t batch = argc > 5 ? (uint32_t)std::atoi(argv[5]) : 16384, reps = argc > 6 ? (uint32_t)std::atoi(argv[6]) : 16;
+  // search policy of the B200 player: fixed batches of 2048 leaves x 16 playouts scored best in self-play
+  // (profiles/r02i_search_policy_selfplay.jsonl); scale > 0 lets the batch grow with the tree
+  const uint32_t batch = argc > 5 ? (uint32_t)std::atoi(argv[5]) : 2048, reps = argc > 6 ? (uint32_t)std::atoi(argv[6]) : 16;
+  const float scale = argc > 7 ? (float)std::atof(argv[7]) : 0.0f;
   int score[3] = {0, 0, 0};  // A wins, mcts_host wins, draws
   const char *name_a = mode == "b200" ? "b200_tree" : mode == "hybrid" ? "mcts_hybrid(drop-in)" : "mcts_device_multiple(drop-in)";
   for (int g = 0; g < games; g++) {
@@ -128,7 +132,7 @@ int main(int argc, char **argv) {
     std::unique_ptr<Player> players[NUM_PLAYERS];
     const int seat_a = g % 2;  // colours alternate
     if (mode == "b200") {
-      mine = new B200TreePlayer(seconds_a, batch, reps);
+      mine = new B200TreePlayer(seconds_a, batch, reps, scale);
       players[seat_a] = std::unique_ptr<Player>(mine);
     } else if (mode == "hybrid") {
       players[seat_a] = std::make_unique<MCTSPlayer>(50, 0.02f, (unsigned)seconds_a, std::make_unique<HybridPlayoutDriver>(1.2f));
