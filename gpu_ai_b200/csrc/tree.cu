@@ -194,7 +194,7 @@ void give_block(void *p) {
 }
 
 // where a thread allocates: a private range inside one arena block
-struct Cursor {
+struct alignas(64) Cursor {  // one cache line each: neighbours in a vector are written by different threads
   uint32_t next = 0, end = 0;
   uint64_t made = 0;
 };
@@ -250,6 +250,12 @@ struct Visit {
 };
 struct Item {  // a subtree handed to a worker thread
   uint32_t node, trials, off;
+  uint32_t worker, vbegin, vend;  // its visit records: [vbegin, vend) of that worker's list for the batch's slot
+};
+// per-thread scratch of the parallel walks, one cache line apart (the record lists are appended to on every node
+// visit: vector headers side by side would ping-pong between the cores)
+struct alignas(64) WorkerLists {
+  std::vector<Visit> visits[kPipeSlots];
 };
 
 struct Batch {
@@ -257,8 +263,8 @@ struct Batch {
   uint64_t pid_base = 0, key = 0;
   std::vector<Visit> top;                   // visits above the items (handled by the calling thread)
   std::vector<Item> items;                  // disjoint subtrees, ascending leaf offset, covering [0, n)
-  std::vector<std::vector<Visit>> visits;   // per item
   std::vector<uint64_t> sum1, sum2;         // per item: wins of its leaf range
+  int slot = 0;
   double t_launch = 0;
 };
 
@@ -273,6 +279,7 @@ double now_s() {
 struct b2p_tree {
   Arena *arena = new Arena();
   std::vector<Cursor> cursors = std::vector<Cursor>(1);  // [0] = calling thread, [1 + w] = search worker w
+  std::vector<WorkerLists> lists;
   uint32_t root = 0;
   uint32_t epoch = 0;
   std::string err;
@@ -522,7 +529,7 @@ struct b2p_tree {
   void top_select(uint32_t id, uint32_t trials, uint32_t off, int depth, uint32_t grain, Batch &b, const SelCtx &c) {
     Node &nd = at(id);
     if (trials <= grain || depth >= 5 || !descend(nd, trials, *c.cur)) {
-      b.items.push_back({id, trials, off});
+      b.items.push_back({id, trials, off, 0u, 0u, 0u});
       return;
     }
     b.top.push_back({id, off, off + trials});
@@ -539,26 +546,32 @@ struct b2p_tree {
   }
 
   void select_batch(Batch &b, uint32_t n, uint32_t reps, b2p_state16 *leaves, size_t threads, bool exact) {
+    b.slot = (int)(&b - batch);
     b.n = n;
     b.top.clear();
     b.items.clear();
     if (n == 0) return;
     if (cursors.size() < threads + 1) cursors.resize(threads + 1);
+    if (lists.size() < threads) lists.resize(threads);
     const uint32_t grain = std::max<uint32_t>(64u, n / (uint32_t)(threads * 16));
     SelCtx c0{&cursors[0], &b.top, leaves, reps, exact};
     top_select(root, n, 0, 0, threads <= 1 ? n : grain, b, c0);
-    if (b.visits.size() < b.items.size()) b.visits.resize(b.items.size());
     b.sum1.assign(b.items.size(), 0);
     b.sum2.assign(b.items.size(), 0);
     std::atomic<size_t> next{0}, worker_id{0};
     auto work = [&]() {
       const size_t me = worker_id.fetch_add(1);
+      std::vector<Visit> &mine = lists[me].visits[b.slot];
+      mine.clear();
+      SelCtx c{&cursors[1 + me], &mine, leaves, reps, exact};
       for (;;) {
         const size_t k = next.fetch_add(1);
         if (k >= b.items.size()) return;
-        b.visits[k].clear();
-        SelCtx c{&cursors[1 + me], &b.visits[k], leaves, reps, exact};
-        fast_select(b.items[k].node, b.items[k].trials, b.items[k].off, c);
+        Item &it = b.items[k];
+        it.worker = (uint32_t)me;
+        it.vbegin = (uint32_t)mine.size();
+        fast_select(it.node, it.trials, it.off, c);
+        it.vend = (uint32_t)mine.size();
       }
     };
     pool.run(std::min(threads, b.items.size()), work);
@@ -585,8 +598,8 @@ struct b2p_tree {
         }
         b.sum1[k] = a;
         b.sum2[k] = c;
-        const std::vector<Visit> &vs = b.visits[k];
-        const size_t nv = vs.size();
+        const Visit *vs = lists[it.worker].visits[b.slot].data() + it.vbegin;
+        const size_t nv = it.vend - it.vbegin;
         for (size_t v = 0; v < nv; v++) {
           if (v + 8 < nv) __builtin_prefetch(&at(vs[v + 8].node), 1);
           const Visit &vi = vs[v];
@@ -794,7 +807,7 @@ int b2p_tree_search_ex(b2p_ctx *ctx, b2p_tree *t, const b2p_search_opts *o, b2p_
     return B2P_OK;
   }
   const unsigned hw = std::thread::hardware_concurrency();
-  const size_t threads = o->threads > 0 ? (size_t)o->threads : std::max<size_t>(1, std::min<size_t>(hw ? hw : 1, 16));
+  const size_t threads = o->threads > 0 ? (size_t)o->threads : std::max<size_t>(1, std::min<size_t>(hw ? hw : 1, 32));
   const int depth = o->depth <= 0 ? 2 : std::min(o->depth, kPipeSlots);
   // one launch holds fewer than 2^31 playouts per device; a batch also never exceeds max_batch leaves
   uint64_t cap = o->max_batch ? o->max_batch : (1u << 20);

@@ -225,7 +225,7 @@ typedef struct b2p_search_opts {
   uint32_t reps;          /* playouts per selected leaf */
   int mode;               /* B2P_MODE_* */
   uint64_t key;           /* Philox key of round r = key + r; playout ids count up over the whole search */
-  int threads;            /* host threads for select/update; 0 = min(hardware threads, 16) */
+  int threads;            /* host threads for select/update; 0 = min(hardware threads, 32) */
   int depth;              /* batches in flight: 1 serial, 2..4 pipelined; 0 = 2 */
 } b2p_search_opts;
 typedef struct b2p_search_stats {
