@@ -25,6 +25,7 @@
 #include <vector>
 
 #include "hostpool.h"
+#include "pack776.h"
 #include "kernels.cuh"
 
 using namespace b2p;
@@ -154,37 +155,6 @@ bool mode_to_kernel(int mode, int order, KernelMode *out) {
 // ---- reference layout (probed: SURVEY.md 8a) ---------------------------------------------------
 constexpr size_t kStateBytes = 776, kItemBytes = 12, kTurnOff = 768, kMscOff = 772;
 constexpr size_t kMoveBytes = 38;
-
-// Branch-free: per dark square one 8-byte load (occupied @0, type @4) and one 4-byte load (owner @8);
-// type/owner only count where `occupied` is set (State::move leaves stale fields in vacated squares).
-inline void pack_one(const unsigned char *s, b2p_state16 *o) {
-  uint32_t occ = 0, p2 = 0, k = 0;
-  for (int r = 0; r < 8; r++) {
-    const unsigned char *row = s + 8 * kItemBytes * (size_t)r + kItemBytes * (size_t)((r & 1) ^ 1);
-    for (int j = 0; j < 4; j++) {
-      const unsigned char *q = row + 2 * kItemBytes * (size_t)j;
-      uint64_t w;
-      uint32_t owner;
-      std::memcpy(&w, q, 8);
-      std::memcpy(&owner, q + 8, 4);
-      const uint32_t oc = (uint32_t)(w & 0xFFu) != 0u;  // BoardItem::occupied
-      const uint32_t ty = (uint32_t)(w >> 32) == 1u;    // CHECKER_KING
-      const uint32_t ow = owner != 0u;                  // PLAYER_2
-      const int i = r * 4 + j;
-      occ |= oc << i;
-      p2 |= (oc & ow) << i;
-      k |= (oc & ty) << i;
-    }
-  }
-  int32_t turn;
-  uint32_t msc;
-  std::memcpy(&turn, s + kTurnOff, 4);
-  std::memcpy(&msc, s + kMscOff, 4);
-  o->p1 = occ & ~p2;
-  o->p2 = p2;
-  o->kings = k;
-  o->meta = (turn == 1 ? 1u : 0u) | (std::min<uint32_t>(msc, 0xFFFFFFu) << 8);
-}
 
 inline void unpack_one(const b2p_state16 *p, unsigned char *s) {
   std::memset(s, 0, kStateBytes);
@@ -381,10 +351,12 @@ int b2p_pack776(const void *states, size_t n, b2p_state16 *out) {
   if (n && (!states || !out)) return B2P_EINVAL;
   const unsigned char *s = (const unsigned char *)states;
   parallel_for(n, 8192, [&](size_t lo, size_t hi) {
-    for (size_t i = lo; i < hi; i++) pack_one(s + kStateBytes * i, out + i);
+    pack776_range(s + kStateBytes * lo, hi - lo, out + lo);
   });
   return B2P_OK;
 }
+
+const char *b2p_pack776_impl(void) { return pack776_impl(); }
 
 int b2p_unpack776(const b2p_state16 *states, size_t n, void *states_out) {
   if (n && (!states || !states_out)) return B2P_EINVAL;
@@ -766,7 +738,7 @@ int b2p_run_states776(b2p_ctx *ctx, const void *states, size_t n, int mode, int 
       const Shard sh = shard_of(n, sg.g, G);
       b2p_state16 *stage = (b2p_state16 *)d.h_states.ptr + sg.lo + tk.lo;
       const unsigned char *from = src + kStateBytes * (sh.lo + sg.lo + tk.lo);
-      for (size_t i = 0; i < tk.len; i++) pack_one(from + kStateBytes * i, stage + i);
+      pack776_range(from, tk.len, stage);
       if (sg.todo.fetch_sub(1) != 1) continue;
       // last task of the segment: queue its GPU work
       std::lock_guard<std::mutex> lock(enqueue_mu);

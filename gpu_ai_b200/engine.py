@@ -53,6 +53,7 @@ ABI = [
     ("b2p_alloc_host", _INT, [C.POINTER(_VP), _SZ]),
     ("b2p_free_host", _INT, [_VP]),
     ("b2p_pack776", _INT, [_VP, _SZ, _VP]),
+    ("b2p_pack776_impl", C.c_char_p, []),
     ("b2p_unpack776", _INT, [_VP, _SZ, _VP]),
     ("b2p_expand_move", _INT, [_U64, _VP]),
     ("b2p_microbench", _INT, [_VP, _INT, _INT, _INT, C.POINTER(C.c_double), C.POINTER(C.c_double)]),

@@ -161,6 +161,9 @@ int b2p_free_host(void *ptr);
  * struct State <-> b2p_state16.  type/owner are read only where `occupied` is set: State::move
  * leaves stale fields in vacated squares (src/state.cu:78-84). */
 int b2p_pack776(const void *states, size_t n, b2p_state16 *out);
+/* which packer this process runs: "avx512bw+bmi2" (one VPTESTMB + three PEXT per cache line of the State) or
+ * "scalar"; B2P_PACK_SCALAR=1 in the environment forces the portable one.  Same bits either way. */
+const char *b2p_pack776_impl(void);
 int b2p_unpack776(const b2p_state16 *states, size_t n, void *states_out);
 /* b2p_move_t -> struct Move (38 B: from@0 to@2 removed@4 intermediate@20 jumps@36 promoted@37) */
 int b2p_expand_move(b2p_move_t move, void *move38_out);

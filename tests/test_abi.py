@@ -50,6 +50,44 @@ def test_pack776_ignores_stale_fields_of_vacated_squares(lib, golden):
     assert np.array_equal(engine.pack776(s), golden["leaves_states"][:64])
 
 
+def test_both_packers_give_the_same_bits(lib, port):
+    """The reference-facing call packs 776-byte States with AVX-512BW + BMI2 where the CPU has them and with a
+    portable scalar loop elsewhere (gpu_ai_b200/csrc/pack776.cpp): both against the oracle's converter on 100 000
+    reachable positions with garbage in every field the reference leaves stale (type / owner of vacated squares,
+    including PLAYER_NONE = -1 owners) and in the padding bytes of `bool occupied`."""
+    import os
+    import subprocess
+    import sys
+    code = r"""
+import sys, numpy as np
+sys.path.insert(0, %r)
+import gpu_ai_b200 as b
+from gpu_ai_b200 import engine
+from oracle.pyoracle import Checker
+port = Checker("port")
+leaves = np.concatenate([port.gen_leaves(60000, key=5), np.load(%r)["synth_states"]])
+s = port.unpack776(leaves).reshape(-1, 64 * 12 + 8)
+board = s[:, :768].reshape(-1, 64, 12)
+rng = np.random.default_rng(1)
+occ = board[:, :, 0] != 0
+for byte in (4, 8, 9, 10, 11):
+    junk = rng.integers(0, 256, size=occ.shape).astype(np.uint8)
+    board[:, :, byte] = np.where(occ, board[:, :, byte], junk if byte != 4 else junk & 1)
+for byte in (1, 2, 3):
+    board[:, :, byte] = rng.integers(0, 256, size=occ.shape).astype(np.uint8)
+out = engine.pack776(s)
+assert np.array_equal(out, leaves), "packer mismatch"
+print(b.load_library().b2p_pack776_impl().decode())
+""" % (ROOT, os.path.join(ROOT, "tests", "golden", "reference_vectors.npz"))
+    seen = set()
+    for force in ("0", "1"):
+        r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, B2P_PACK_SCALAR=force), stdout=subprocess.PIPE,
+                           stderr=subprocess.PIPE, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        seen.add(r.stdout.strip().splitlines()[-1])
+    assert "scalar" in seen and seen <= {"scalar", "avx512bw+bmi2"}
+
+
 def test_expand_move_matches_reference_move_layout(lib, golden):
     # Move: from@0 to@2 removed@4.. intermediate@20.. jumps@36 promoted@37 (38 bytes)
     from gpu_ai_b200 import engine
