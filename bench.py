@@ -51,7 +51,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b2p", choices=["b2p", "reference"])
-    ap.add_argument("--reps", type=int, default=32, help="playouts per leaf per step")
+    ap.add_argument("--reps", type=int, default=64, help="playouts per leaf per step")
     ap.add_argument("--leaves", type=int, default=LEAVES_PER_GPU, help="leaves per GPU")
     ap.add_argument("--mode", default="random", choices=["random", "heuristic"])
     ap.add_argument("--order", default="fast", choices=["fast", "canonical"])

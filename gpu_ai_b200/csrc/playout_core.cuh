@@ -279,32 +279,37 @@ B2P_HD int capture_shape(const Pos &p, const JumpMasks &jm, const uint32_t cap[4
   return shape;
 }
 
+// A capture that starts with a hop onto the single-bit mask `land` on a shape-1 ply: follows the forced
+// continuation (men: up to two more hops, never a choice; kings: one forced second hop -- shape 1 guarantees there
+// is no third), accumulating the jumped squares.  All single-bit masks, no bit indices.
+B2P_HD void follow_forced_chain(const JumpMasks &jm, bool man, uint32_t &land, uint32_t &cap) {
+  if (!man) {
+    const uint32_t nib = ((jm.j[0] & land) ? 1u : 0u) | ((jm.j[1] & land) ? 2u : 0u) | ((jm.j[2] & land) ? 4u : 0u) |
+                         ((jm.j[3] & land) ? 8u : 0u);
+    if (nib) {
+      const int d2 = lowbit(nib);
+      cap |= step_mask(land, d2);
+      land = jump_mask(land, d2);
+    }
+  } else {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int hop = 0; hop < 2; hop++) {  // a man makes at most 3 hops
+      if (!((jm.j[0] | jm.j[1]) & land)) break;
+      const int d2 = (jm.j[1] & land) ? 1 : 0;  // 1 = UL, 0 = UR (exactly one is available)
+      cap |= step_mask(land, d2);
+      land = jump_mask(land, d2);
+    }
+  }
+}
+
 // shapes 0 and 1: the move list has one entry per first hop (or step).  Returns the number of legal moves.
 template <int ORDER>
 B2P_HD int pick_first_hop_and_chain(const Pos &p, const PlyMasks &m, int shape, uint32_t turn, uint32_t r, uint32_t &from,
                                     uint32_t &to, uint32_t &captured) {
   const int n = pick_single_hop<ORDER>(p, m, turn, r, from, to, captured);
-  if (n != 0 && shape == 1) {
-    int cur = lowbit(to);
-    if (p.kings & from) {
-      // king: at most one forced second hop (shape 1 guarantees there is no third)
-      const uint32_t nib = ((m.jm.j[0] >> cur) & 1u) | (((m.jm.j[1] >> cur) & 1u) << 1) | (((m.jm.j[2] >> cur) & 1u) << 2) |
-                           (((m.jm.j[3] >> cur) & 1u) << 3);
-      if (nib) {
-        const int d = lowbit(nib);
-        captured |= 1u << step_target(cur, d);
-        cur = jump_target(cur, d);
-      }
-    } else {
-      // man: forced continuation, at most two more hops, never a choice
-      while (((m.jm.j[0] | m.jm.j[1]) >> cur) & 1u) {
-        const int d = (int)((m.jm.j[1] >> cur) & 1u);  // 1 = UL, 0 = UR (exactly one is available)
-        captured |= 1u << step_target(cur, d);
-        cur = jump_target(cur, d);
-      }
-    }
-    to = 1u << cur;
-  }
+  if (n != 0 && shape == 1) follow_forced_chain(m.jm, !(p.kings & from), to, captured);
   return n;
 }
 
@@ -371,31 +376,6 @@ B2P_HD uint32_t noise_half(const Philox4 &b, int q) {  // 16-bit draw of candida
 // slots (directions, reference order) of the four candidate masks present at origin o, as a 4-bit value
 B2P_HD uint32_t slots_at(const uint32_t a[4], int o) {
   return ((a[0] >> o) & 1u) | (((a[1] >> o) & 1u) << 1) | (((a[2] >> o) & 1u) << 2) | (((a[3] >> o) & 1u) << 3);
-}
-
-// A capture that starts with hop (o --d--> land) on a shape-0/1 ply: follows the forced continuation, if any
-// (men: up to two more hops, never a choice; kings: one forced second hop), accumulating the jumped squares.
-B2P_HD void follow_forced_chain(const JumpMasks &jm, bool man, int shape, int &land, uint32_t &cap) {
-  if (shape != 1) return;
-  if (!man) {
-    const uint32_t nib = ((jm.j[0] >> land) & 1u) | (((jm.j[1] >> land) & 1u) << 1) | (((jm.j[2] >> land) & 1u) << 2) |
-                         (((jm.j[3] >> land) & 1u) << 3);
-    if (nib) {
-      const int d2 = lowbit(nib);
-      cap |= 1u << step_target(land, d2);
-      land = jump_target(land, d2);
-    }
-  } else {
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int hop = 0; hop < 2; hop++) {  // a man makes at most 3 hops
-      if (!(((jm.j[0] | jm.j[1]) >> land) & 1u)) break;
-      const int d2 = (int)((jm.j[1] >> land) & 1u);  // 1 = UL, 0 = UR (exactly one is available)
-      cap |= 1u << step_target(land, d2);
-      land = jump_target(land, d2);
-    }
-  }
 }
 
 // Staged for SIMT: every lane of the calling group walks through the same stages, and the group is
@@ -486,14 +466,15 @@ B2P_HD int heuristic_ply(Game &g, unsigned lanes, NoiseBlock &&noise_block, Gaus
     int cached = 0;
     for (int k = 0; k < n; k++) {
       const int slot = lowbit(nib);
-      const bool man = (ownMen >> o) & 1u;
+      const uint32_t fbit = 1u << o;
+      const bool man = (ownMen & fbit) != 0u;
       const int d = (m.capture && man) ? (slot ^ 1) : slot;
-      const int mid = step_target(o, d);
-      int land = m.capture ? jump_target(o, d) : mid;
-      uint32_t cap = m.capture ? (1u << mid) : 0u;
-      follow_forced_chain(m.jm, man, shape, land, cap);
+      const uint32_t mid = step_mask(fbit, d);
+      uint32_t land = m.capture ? jump_mask(fbit, d) : mid;
+      uint32_t cap = m.capture ? mid : 0u;
+      if (shape == 1) follow_forced_chain(m.jm, man, land, cap);
       const int idx = rev ? n - 1 - k : k;
-      const uint32_t promo = (man && land >= 28) ? 3u : 0u;
+      const uint32_t promo = (man && (land & 0xF0000000u)) ? 3u : 0u;
       const uint32_t loss = (uint32_t)(popc(cap) + 3 * popc(cap & p.kings));
       if ((idx >> 3) != cached) { cached = idx >> 3; nb = noise_block(cached); }  // more than 8 candidates: rare
       const float w = ratio(my + promo, his - loss) + gauss(noise_half(nb, idx & 7));
@@ -561,16 +542,16 @@ B2P_HD int heuristic_ply(Game &g, unsigned lanes, NoiseBlock &&noise_block, Gaus
   if (!dfs) {
     const int pick = rev ? n - 1 - best.idx : best.idx;
     const int sel = select_origin_major(a, n > 0 ? pick : 0);
-    const int o = sel & 31;
+    const uint32_t fbit = 1u << (sel & 31);
     const int slot = (sel >> 5) & 3;
-    const bool man = (ownMen >> o) & 1u;
+    const bool man = (ownMen & fbit) != 0u;
     const int d = (m.capture && man) ? (slot ^ 1) : slot;
-    const int mid = step_target(o, d) & 31;
-    int land = m.capture ? (jump_target(o, d) & 31) : mid;
-    uint32_t cap = m.capture ? (1u << mid) : 0u;
-    follow_forced_chain(m.jm, man, shape, land, cap);
-    from = 1u << o;
-    to = 1u << (land & 31);
+    const uint32_t mid = step_mask(fbit, d);
+    uint32_t land = m.capture ? jump_mask(fbit, d) : mid;
+    uint32_t cap = m.capture ? mid : 0u;
+    if (shape == 1) follow_forced_chain(m.jm, man, land, cap);
+    from = fbit;
+    to = land;
     captured = cap;
   }
 

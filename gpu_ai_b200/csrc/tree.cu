@@ -413,6 +413,42 @@ struct b2p_tree {
     return assigned;
   }
 
+  // B2P_POLICY_UCT: the node's trials go down ONE BY ONE, each to the child with the highest UCB1 value, every
+  // assigned trial counting at once as `reps` visits without a win (virtual loss).  This is what a strictly
+  // sequential UCT search does with the same budget; the reference's rule above shares a batch out in proportion
+  // to the UCB1 values, which are all of the same size (0.4 ... 1.5), i.e. almost uniformly -- with batches of
+  // thousands of leaves it explores the first tree levels breadth-first however good or bad a move looks
+  // (measured: 300x the playouts of mcts_host buy a 57 % score, profiles/r02m_*).  Cost: trials x children
+  // comparisons per node, one weight update per trial.
+  uint32_t distribute_uct(const Node &nd, uint32_t trials, uint32_t reps, uint32_t *child_trials) const {
+    const uint32_t nc = nd.n_children, fc = nd.first_child;
+    float w[kMaxMoves], wins[kMaxMoves], tot[kMaxMoves];
+    const float two_log = 2.0f * logf((float)(nd.total > 1 ? nd.total : 2) + (float)trials * (float)reps);
+    // a move is as good as the share of playouts through it that the player MAKING it wins.  (GameTree::ucb1,
+    // src/mcts.cpp:182-191, reads wins[state.turn] of the CHILD -- the opponent's wins; under its near-uniform
+    // allocation that hardly shows, and the serial interface reproduces it for parity.  Under UCT it would steer
+    // the search towards the mover's worst moves.)
+    const unsigned mover = nd.state.meta & 1u;
+    for (uint32_t i = 0; i < nc; i++) {
+      const Node &c = at(fc + i);
+      wins[i] = (float)(int64_t)c.wins[mover];
+      tot[i] = (float)(int64_t)c.total;
+      w[i] = c.total == 0 ? INFINITY : wins[i] / tot[i] + sqrtf(two_log / tot[i]);
+      child_trials[i] = 0;
+    }
+    const float step = (float)reps;
+    for (uint32_t t = 0; t < trials; t++) {
+      uint32_t best = 0;
+      float bw = w[0];
+      for (uint32_t i = 1; i < nc; i++)
+        if (w[i] > bw) { bw = w[i]; best = i; }
+      child_trials[best]++;
+      tot[best] += step;
+      w[best] = wins[best] / tot[best] + sqrtf(two_log / tot[best]);
+    }
+    return trials;
+  }
+
   uint32_t assigned_of(const Node &n) const { return n.epoch == epoch ? n.assigned : 0u; }
 
   // ---- the reference's serial interface ---------------------------------------------------------------------
@@ -495,8 +531,13 @@ struct b2p_tree {
     std::vector<Visit> *visits;
     b2p_state16 *leaves;
     uint32_t reps;
-    bool exact;
+    int policy;  // 0: reference rule, reference arithmetic; 1: reference rule, single precision; 2: UCT
   };
+
+  uint32_t hand_down(const Node &nd, uint32_t trials, uint32_t *child_trials, const SelCtx &c) const {
+    if (c.policy == 2) return distribute_uct(nd, trials, c.reps, child_trials);
+    return c.policy == 0 ? distribute<true>(nd, trials, child_trials) : distribute<false>(nd, trials, child_trials);
+  }
 
   void emit_leaf(Node &nd, uint32_t trials, uint32_t off, const SelCtx &c) {
     for (uint32_t i = 0; i < trials; i++) c.leaves[off + i] = nd.state;
@@ -514,7 +555,7 @@ struct b2p_tree {
       return;
     }
     uint32_t child_trials[kMaxMoves];
-    const uint32_t given = c.exact ? distribute<true>(nd, trials, child_trials) : distribute<false>(nd, trials, child_trials);
+    const uint32_t given = hand_down(nd, trials, child_trials, c);
     if (given < trials) child_trials[0] += trials - given;  // never in practice (see distribute); keeps leaf indices dense
     nd.total += (uint64_t)trials * c.reps;
     const uint32_t nc = nd.n_children, fc = nd.first_child;
@@ -534,7 +575,7 @@ struct b2p_tree {
     }
     b.top.push_back({id, off, off + trials});
     uint32_t child_trials[kMaxMoves];
-    const uint32_t given = c.exact ? distribute<true>(nd, trials, child_trials) : distribute<false>(nd, trials, child_trials);
+    const uint32_t given = hand_down(nd, trials, child_trials, c);
     if (given < trials) child_trials[0] += trials - given;
     nd.total += (uint64_t)trials * c.reps;
     const uint32_t nc = nd.n_children, fc = nd.first_child;
@@ -545,7 +586,7 @@ struct b2p_tree {
     }
   }
 
-  void select_batch(Batch &b, uint32_t n, uint32_t reps, b2p_state16 *leaves, size_t threads, bool exact) {
+  void select_batch(Batch &b, uint32_t n, uint32_t reps, b2p_state16 *leaves, size_t threads, int policy) {
     b.slot = (int)(&b - batch);
     b.n = n;
     b.top.clear();
@@ -554,7 +595,7 @@ struct b2p_tree {
     if (cursors.size() < threads + 1) cursors.resize(threads + 1);
     if (lists.size() < threads) lists.resize(threads);
     const uint32_t grain = std::max<uint32_t>(64u, n / (uint32_t)(threads * 16));
-    SelCtx c0{&cursors[0], &b.top, leaves, reps, exact};
+    SelCtx c0{&cursors[0], &b.top, leaves, reps, policy};
     top_select(root, n, 0, 0, threads <= 1 ? n : grain, b, c0);
     b.sum1.assign(b.items.size(), 0);
     b.sum2.assign(b.items.size(), 0);
@@ -563,7 +604,7 @@ struct b2p_tree {
       const size_t me = worker_id.fetch_add(1);
       std::vector<Visit> &mine = lists[me].visits[b.slot];
       mine.clear();
-      SelCtx c{&cursors[1 + me], &mine, leaves, reps, exact};
+      SelCtx c{&cursors[1 + me], &mine, leaves, reps, policy};
       for (;;) {
         const size_t k = next.fetch_add(1);
         if (k >= b.items.size()) return;
@@ -695,6 +736,29 @@ int b2p_tree_best_move(const b2p_tree *t, int player, b2p_move_t *move_out) {
   return B2P_OK;
 }
 
+// The "robust child": the root move with the most trials (ties: the better score for `player`, then the first).
+// The companion of B2P_POLICY_UCT, which visits moves very unevenly: the win rate of a move that was tried a few
+// hundred times is noise next to one that was tried millions of times, and GameTree::getOptMove's "highest rate"
+// picks exactly such outliers.  (With the reference's near-uniform allocation the two rules agree.)
+int b2p_tree_robust_move(const b2p_tree *t, int player, b2p_move_t *move_out) {
+  if (!t || !move_out || player < 0 || player > 1) return B2P_EINVAL;
+  const Node &r = t->at(t->root);
+  if (!r.expanded) return B2P_EINVAL;
+  int opt = -1;
+  uint64_t best_n = 0;
+  double best_s = -INFINITY;
+  for (uint32_t i = 0; i < r.n_children; i++) {
+    Node &c = t->at(r.first_child + i);
+    const double s = c.total ? t->score(c, player) : (b2p_tree::game_over(c) ? t->score(c, player) : 0.0);
+    if (opt < 0 || c.total > best_n || (c.total == best_n && s > best_s)) { opt = (int)i; best_n = c.total; best_s = s; }
+  }
+  if (opt < 0) return B2P_EINVAL;
+  b2p_move_t buf[kMaxMoves];
+  t->root_move_list(buf);
+  *move_out = buf[opt];
+  return B2P_OK;
+}
+
 // GameTree::move (src/mcts.cpp:11-25): keep the chosen subtree (copied breadth-first into a fresh arena, the
 // rest of the old tree is freed), or start a new tree from the successor state when the root was never expanded.
 int b2p_tree_move(b2p_tree *t, b2p_move_t move) {
@@ -778,9 +842,10 @@ const char *b2p_tree_last_error(const b2p_tree *t) { return t ? t->err.c_str() :
 
 // The two host halves of one pipelined round (what b2p_tree_search_ex does around b2p_run_counts_async), for a
 // caller that runs the playouts itself.
-int b2p_tree_select_batch(b2p_tree *t, int slot, uint32_t trials, uint32_t reps, int threads, int exact, b2p_state16 *leaves_out) {
+int b2p_tree_select_batch(b2p_tree *t, int slot, uint32_t trials, uint32_t reps, int threads, int policy, b2p_state16 *leaves_out) {
   if (!t || slot < 0 || slot >= kPipeSlots || reps == 0 || (trials && !leaves_out)) return B2P_EINVAL;
-  t->select_batch(t->batch[slot], trials, reps, leaves_out, (size_t)std::max(1, threads), exact != 0);
+  if (policy < 0 || policy > 2) return B2P_EINVAL;
+  t->select_batch(t->batch[slot], trials, reps, leaves_out, (size_t)std::max(1, threads), policy);
   return B2P_OK;
 }
 
@@ -862,7 +927,7 @@ int b2p_tree_search_ex(b2p_ctx *ctx, b2p_tree *t, const b2p_search_opts *o, b2p_
     const int slot = (int)(launched % (uint32_t)depth);
     Batch &b = t->batch[slot];
     const double s0 = now_s();
-    t->select_batch(b, n, o->reps, t->h_leaves[slot], threads, depth == 1);
+    t->select_batch(b, n, o->reps, t->h_leaves[slot], threads, o->policy == B2P_POLICY_UCT ? 2 : (depth == 1 ? 0 : 1));
     st.select_s += now_s() - s0;
     b.pid_base = selected * o->reps;
     b.key = o->key + it;

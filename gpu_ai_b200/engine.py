@@ -64,6 +64,7 @@ ABI = [
     ("b2p_tree_update", _INT, [_VP, _VP, _U32, _U32]),
     ("b2p_tree_update_counts", _INT, [_VP, _VP, _U32, _U32]),
     ("b2p_tree_best_move", _INT, [_VP, _INT, C.POINTER(_U64)]),
+    ("b2p_tree_robust_move", _INT, [_VP, _INT, C.POINTER(_U64)]),
     ("b2p_tree_move", _INT, [_VP, _U64]),
     ("b2p_tree_info", _INT, [_VP, _VP]),
     ("b2p_tree_root_moves", _INT, [_VP, _VP, _VP, _VP, _VP, _U32]),
@@ -227,7 +228,8 @@ class Engine:
 
 class SearchOpts(C.Structure):
     _fields_ = [("iterations", _U32), ("seconds", C.c_double), ("initial_batch", _U32), ("scale", C.c_float),
-                ("max_batch", _U32), ("reps", _U32), ("mode", _INT), ("key", _U64), ("threads", _INT), ("depth", _INT)]
+                ("max_batch", _U32), ("reps", _U32), ("mode", _INT), ("key", _U64), ("threads", _INT), ("depth", _INT),
+                ("policy", _INT)]
 
 
 class SearchStats(C.Structure):
@@ -281,6 +283,11 @@ class Tree:
         self._check(self.lib.b2p_tree_best_move(self.h, player, C.byref(m)))
         return int(m.value)
 
+    def robust_move(self, player):
+        m = _U64()
+        self._check(self.lib.b2p_tree_robust_move(self.h, player, C.byref(m)))
+        return int(m.value)
+
     def move(self, move):
         self._check(self.lib.b2p_tree_move(self.h, int(move)))
 
@@ -304,9 +311,11 @@ class Tree:
         self._check(rc)
         return int(played.value)
 
-    def select_batch(self, slot, trials, reps=1, threads=1, exact=True):
+    def select_batch(self, slot, trials, reps=1, threads=1, exact=True, policy=None):
+        """policy: 0 reference rule / reference arithmetic (exact=True), 1 reference rule / float, 2 UCT"""
         out = np.empty((max(trials, 1), 4), dtype=np.uint32)
-        self._check(self.lib.b2p_tree_select_batch(self.h, slot, trials, reps, threads, int(exact), _ptr(out)))
+        pol = policy if policy is not None else (0 if exact else 1)
+        self._check(self.lib.b2p_tree_select_batch(self.h, slot, trials, reps, threads, pol, _ptr(out)))
         return out[:trials]
 
     def update_batch(self, slot, wins, threads=1):
@@ -314,9 +323,9 @@ class Tree:
         self._check(self.lib.b2p_tree_update_batch(self.h, slot, _ptr(w), threads))
 
     def search_ex(self, engine, iterations=0, seconds=0.0, initial_batch=50, scale=0.02, max_batch=0, reps=1,
-                  mode=MODE_RANDOM, key=1, threads=0, depth=0):
-        """b2p_tree_search_ex: returns the b2p_search_stats as a dict."""
-        o = SearchOpts(iterations, seconds, initial_batch, scale, max_batch, reps, mode, key, threads, depth)
+                  mode=MODE_RANDOM, key=1, threads=0, depth=0, policy=0):
+        """b2p_tree_search_ex: returns the b2p_search_stats as a dict.  policy: 0 reference allocation, 1 UCT."""
+        o = SearchOpts(iterations, seconds, initial_batch, scale, max_batch, reps, mode, key, threads, depth, policy)
         st = SearchStats()
         self._check(self.lib.b2p_tree_search_ex(engine.ctx, self.h, C.byref(o), C.byref(st)))
         return {k: getattr(st, k) for k, _ in SearchStats._fields_}

@@ -32,9 +32,12 @@ class Player:
 
 
 class B200MCTSPlayer(Player):
-    def __init__(self, engine=None, seconds=1.0, initial_batch=8192, scale=0.02, reps=32, mode=_e.MODE_RANDOM, seed=1):
+    def __init__(self, engine=None, seconds=1.0, initial_batch=2048, scale=0.0, reps=16, mode=_e.MODE_RANDOM, seed=1, policy=1):
+        """policy 1 = B2P_POLICY_UCT with the most-tried root move (the strong setting); 0 = the reference's
+        allocation rule and its highest-rate move (GameTree::select / getOptMove)."""
         self.engine = engine or _e.Engine()
         self.seconds, self.initial_batch, self.scale, self.reps, self.mode = seconds, initial_batch, scale, reps, mode
+        self.policy = policy
         self.key = seed
         self.tree = None
         self.playouts = 0
@@ -53,12 +56,15 @@ class B200MCTSPlayer(Player):
         if self.tree is None or not np.array_equal(self.tree.info()["root_state"], state):
             self.tree = _e.Tree(state)  # src/player.cpp:95-97: a position the tree does not know starts a new tree
         self.key += 1
-        self.playouts += self.tree.search(self.engine, seconds=self.seconds, initial_batch=self.initial_batch, scale=self.scale,
-                                          reps=self.reps, mode=self.mode, key=self.key)
+        st = self.tree.search_ex(self.engine, seconds=self.seconds, initial_batch=self.initial_batch, scale=self.scale,
+                                 max_batch=max(self.initial_batch, 1 << 18), reps=self.reps, mode=self.mode, key=self.key,
+                                 policy=self.policy)
+        self.playouts += st["playouts"]
         if verbose:
             info = self.tree.info()
             print("Tree size: %d" % info["total_trials"])
-        return self.tree.best_move(int(state[3] & 1))
+        me = int(state[3] & 1)
+        return self.tree.robust_move(me) if self.policy == 1 else self.tree.best_move(me)
 
     def move(self, move):
         if self.tree is not None:

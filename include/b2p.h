@@ -201,6 +201,8 @@ int b2p_tree_update(b2p_tree *tree, const int8_t *winners, uint32_t n, uint32_t 
 /* the same with per-leaf win counts (b2p_run_counts layout): every selected leaf was played `reps` times */
 int b2p_tree_update_counts(b2p_tree *tree, const uint32_t *wins, uint32_t n, uint32_t reps);
 int b2p_tree_best_move(const b2p_tree *tree, int player, b2p_move_t *move_out);   /* GameTree::getOptMove */
+/* the root move with the most trials (the "robust child"): the move rule that goes with B2P_POLICY_UCT */
+int b2p_tree_robust_move(const b2p_tree *tree, int player, b2p_move_t *move_out);
 int b2p_tree_move(b2p_tree *tree, b2p_move_t move);                      /* GameTree::move (subtree reuse) */
 int b2p_tree_info(const b2p_tree *tree, b2p_tree_stats *out);
 /* root move list with per-child statistics; returns the number of legal root moves */
@@ -219,6 +221,10 @@ int b2p_tree_search(b2p_ctx *ctx, b2p_tree *tree, uint32_t iterations, double se
  * (in-flight trials count as visits without wins).  depth == 1 is the strictly serial loop: it takes exactly the
  * decisions of b2p_tree_select -> b2p_run_counts -> b2p_tree_update_counts, for any `threads` and any number of
  * devices.  Results are deterministic for given options (the time limit only decides how many rounds run). */
+enum { B2P_POLICY_REFERENCE = 0, /* GameTree::select's rule: a node's trials are shared out in proportion to the children's
+                                    UCB1 values (src/mcts.cpp:93-139) */
+       B2P_POLICY_UCT = 1        /* a node's trials go down one by one to the child with the highest UCB1 value, in-flight
+                                    trials counting as visits without wins: what a sequential UCT search does */ };
 typedef struct b2p_search_opts {
   uint32_t iterations;    /* rounds; 0 = until `seconds` */
   double seconds;         /* wall-clock budget; 0 = until `iterations` */
@@ -230,6 +236,7 @@ typedef struct b2p_search_opts {
   uint64_t key;           /* Philox key of round r = key + r; playout ids count up over the whole search */
   int threads;            /* host threads for select/update; 0 = min(hardware threads, 32) */
   int depth;              /* batches in flight: 1 serial, 2..4 pipelined; 0 = 2 */
+  int policy;             /* B2P_POLICY_*: how a node hands its trials to its children */
 } b2p_search_opts;
 typedef struct b2p_search_stats {
   uint64_t playouts, leaves, batches, nodes;
@@ -240,11 +247,11 @@ typedef struct b2p_search_stats {
 } b2p_search_stats;
 /* The two host halves of one pipelined round, for a caller that runs the playouts itself.  select_batch picks
  * `trials` leaves on `threads` host threads (same decisions as b2p_tree_select), counts them into the visited nodes
- * as `reps` trials each and remembers the batch in `slot` (0..3); exact != 0 evaluates UCB1 with the reference's
- * expression types (bit-identical decisions, what depth 1 uses), 0 in single precision (what depth >= 2 uses:
- * a quarter of the cycles); update_batch folds the batch's per-leaf win counts
+ * as `reps` trials each and remembers the batch in `slot` (0..3); policy 0 = the reference's rule with the reference's
+ * expression types (bit-identical decisions, what depth 1 uses), 1 = the same rule in single precision (what
+ * depth >= 2 uses), 2 = B2P_POLICY_UCT; update_batch folds the batch's per-leaf win counts
  * (b2p_run_counts layout) into the nodes it visited.  Several slots may be selected before the first is updated. */
-int b2p_tree_select_batch(b2p_tree *tree, int slot, uint32_t trials, uint32_t reps, int threads, int exact,
+int b2p_tree_select_batch(b2p_tree *tree, int slot, uint32_t trials, uint32_t reps, int threads, int policy,
                           b2p_state16 *leaves_out);
 int b2p_tree_update_batch(b2p_tree *tree, int slot, const uint32_t *wins, int threads);
 int b2p_tree_search_ex(b2p_ctx *ctx, b2p_tree *tree, const b2p_search_opts *opts, b2p_search_stats *stats_out);

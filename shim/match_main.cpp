@@ -1,6 +1,6 @@
 // shim/match_main.cpp -- BASELINE config 5: game-play tournaments against the reference's own `mcts_host` player.
 //
-//   match_b200 <mode> <games> <seconds A> <seconds B (whole seconds)> [batch] [reps] [scale]
+//   match_b200 <mode> <games> <seconds A> <seconds B (whole seconds)> [batch] [reps] [scale] [policy: 1 UCT (default), 0 reference]
 //
 //   mode b200    side A = a Player that searches with b2p_tree_search_ex on the B200s (<seconds A> per move, fractional)
 //   mode hybrid  side A = the reference's `mcts_hybrid` preset (MCTSPlayer(50, 0.02, T, HybridPlayoutDriver(1.2)),
@@ -39,7 +39,8 @@ b2p_move_t encode(const Move &m) {
 
 class B200TreePlayer : public Player {
  public:
-  B200TreePlayer(double seconds, uint32_t batch, uint32_t reps, float scale) : seconds(seconds), batch(batch), reps(reps), scale(scale) {
+  B200TreePlayer(double seconds, uint32_t batch, uint32_t reps, float scale, int policy)
+      : seconds(seconds), batch(batch), reps(reps), scale(scale), policy(policy) {
     if (b2p_create(&ctx, nullptr, 0, 12345) != B2P_OK) throw std::runtime_error(b2p_last_error(nullptr));
     reset();
   }
@@ -59,6 +60,7 @@ class B200TreePlayer : public Player {
     o.max_batch = 1u << 18;
     o.reps = reps;
     o.mode = B2P_MODE_RANDOM;
+    o.policy = policy;
     o.key = key++;
     b2p_search_stats st;
     if (b2p_tree_search_ex(ctx, tree, &o, &st) != B2P_OK) throw std::runtime_error(b2p_tree_last_error(tree));
@@ -67,7 +69,10 @@ class B200TreePlayer : public Player {
     b2p_tree_stats ts;
     b2p_tree_info(tree, &ts);
     b2p_move_t best;
-    if (b2p_tree_best_move(tree, (int)(ts.root_state.meta & 1u), &best) != B2P_OK) throw std::runtime_error("no best move");
+    const int me = (int)(ts.root_state.meta & 1u);
+    // UCT visits moves unevenly: play the most-tried one; the reference allocation goes with the reference's rule
+    if ((policy == B2P_POLICY_UCT ? b2p_tree_robust_move(tree, me, &best) : b2p_tree_best_move(tree, me, &best)) != B2P_OK)
+      throw std::runtime_error("no best move");
     Move m;
     b2p_expand_move(best, &m);
     return m;
@@ -88,6 +93,7 @@ class B200TreePlayer : public Player {
   double seconds;
   uint32_t batch, reps;
   float scale;
+  int policy;
   uint64_t key = 1;
   b2p_ctx *ctx = nullptr;
   b2p_tree *tree = nullptr;
@@ -125,6 +131,7 @@ int main(int argc, char **argv) {
   // (profiles/r02i_search_policy_selfplay.jsonl); scale > 0 lets the batch grow with the tree
   const uint32_t batch = argc > 5 ? (uint32_t)std::atoi(argv[5]) : 2048, reps = argc > 6 ? (uint32_t)std::atoi(argv[6]) : 16;
   const float scale = argc > 7 ? (float)std::atof(argv[7]) : 0.0f;
+  const int policy = argc > 8 ? std::atoi(argv[8]) : B2P_POLICY_UCT;  // 0 = the reference's allocation rule
   int score[3] = {0, 0, 0};  // A wins, mcts_host wins, draws
   const char *name_a = mode == "b200" ? "b200_tree" : mode == "hybrid" ? "mcts_hybrid(drop-in)" : "mcts_device_multiple(drop-in)";
   for (int g = 0; g < games; g++) {
@@ -132,7 +139,7 @@ int main(int argc, char **argv) {
     std::unique_ptr<Player> players[NUM_PLAYERS];
     const int seat_a = g % 2;  // colours alternate
     if (mode == "b200") {
-      mine = new B200TreePlayer(seconds_a, batch, reps, scale);
+      mine = new B200TreePlayer(seconds_a, batch, reps, scale, policy);
       players[seat_a] = std::unique_ptr<Player>(mine);
     } else if (mode == "hybrid") {
       players[seat_a] = std::make_unique<MCTSPlayer>(50, 0.02f, (unsigned)seconds_a, std::make_unique<HybridPlayoutDriver>(1.2f));
@@ -172,7 +179,8 @@ int main(int argc, char **argv) {
                half = z * std::sqrt(ph * (1 - ph) / n + z * z / (4 * n * n)) / den;
   std::cout << "{\"summary\": {\"a\": \"" << name_a << "\", \"a_wins\": " << score[0] << ", \"mcts_host_wins\": " << score[1] << ", \"draws\": " << score[2]
             << ", \"games\": " << games << ", \"a_score_rate\": " << ph << ", \"wilson95\": [" << centre - half << ", " << centre + half << "]}"
-            << ", \"a_seconds_per_move\": " << seconds_a << ", \"mcts_host_seconds_per_move\": " << seconds_b
+            << ", \"a_policy\": \"" << (mode == "b200" ? (policy == B2P_POLICY_UCT ? "uct + most-tried move" : "reference allocation + best-rate move") : "reference")
+            << "\", \"a_seconds_per_move\": " << seconds_a << ", \"mcts_host_seconds_per_move\": " << seconds_b
             << ", \"mcts_host\": \"reference preset MCTSPlayer(50, 0, T, HostPlayoutDriver), pondering on all host cores\"}" << std::endl;
   return 0;
 }

@@ -215,3 +215,50 @@ def test_batch_pipeline_two_in_flight_is_consistent_and_deterministic():
         runs.append((tr.copy(), w1.copy(), w2.copy(), info["nodes"]))
     for x, y in zip(runs[0], runs[1]):
         assert np.array_equal(x, y)
+
+
+def test_uct_policy_is_consistent_deterministic_and_stronger(port):
+    """B2P_POLICY_UCT (trials one by one to the best UCB1 child from the MOVER's point of view, virtual loss, most-tried
+    root move) against the reference's allocation rule (shares in proportion to UCB1 values that read the opponent's
+    wins, src/mcts.cpp:93-139,182-191; best-rate root move) at the SAME budget -- 1500 trials per move in batches of
+    50, one CPU-oracle playout per leaf.  Bookkeeping first, then six games with alternating colours."""
+    import gpu_ai_b200 as b
+    from oracle.pyoracle import ORDER_FAST
+    t = b.Tree(START_PACKED)
+    for it, n in enumerate([50, 700, 3000, 50]):
+        leaves = t.select_batch(it % 2, n, reps=2, threads=3, policy=2)
+        assert len(leaves) == n
+        t.update_batch(it % 2, fake_counts(leaves, 2, it), threads=3)
+    mv, tr, w1, w2 = t.root_moves()
+    assert tr.sum() == 2 * 3800 and ((w1 + w2) <= tr).all() and t.robust_move(0) in set(int(x) for x in mv)
+    t2 = b.Tree(START_PACKED)
+    for it, n in enumerate([50, 700, 3000, 50]):
+        leaves = t2.select_batch(it % 2, n, reps=2, threads=1, policy=2)
+        t2.update_batch(it % 2, fake_counts(leaves, 2, it), threads=1)
+    assert np.array_equal(t2.root_moves()[1], tr)          # same tree for any thread count
+
+    def think(tree, policy, key):
+        for it in range(30):
+            leaves = tree.select_batch(0, 50, reps=1, threads=1, policy=policy)
+            w, _, _, _ = port.playouts(leaves, key=key + it, order=ORDER_FAST)
+            tree.update_batch(0, np.stack([w == 0, w == 1], axis=1).astype(np.uint32), threads=1)
+
+    points = 0.0
+    for g in range(6):
+        uct_seat = g % 2
+        trees = [b.Tree(START_PACKED), b.Tree(START_PACKED)]
+        plies = 0
+        while True:
+            info = trees[0].info()
+            st = info["root_state"]
+            turn, msc = int(st[3] & 1), int(st[3] >> 8)
+            if info["root_moves"] == 0 or msc >= 50:
+                points += 0.5 if msc >= 50 else (1.0 if (turn ^ 1) == uct_seat else 0.0)
+                break
+            uct = turn == uct_seat
+            think(trees[turn], 2 if uct else 0, key=10000 * g + 100 * plies)
+            m = trees[turn].robust_move(turn) if uct else trees[turn].best_move(turn)
+            for tr_ in trees:
+                tr_.move(m)
+            plies += 1
+    assert points >= 4.5, points

@@ -20,12 +20,11 @@ seconds = float(sys.argv[2]) if len(sys.argv) > 2 else 0.1
 opp_trials = int(sys.argv[3]) if len(sys.argv) > 3 else 100000
 eng = b.Engine(devices=1)
 CANDIDATES = {
-    "b16384_grow_2^18_r16": dict(initial_batch=16384, scale=0.02, max_batch=1 << 18, reps=16, depth=2),
-    "b8192_grow_2^16_r8": dict(initial_batch=8192, scale=0.02, max_batch=1 << 16, reps=8, depth=2),
-    "b4096_r32": dict(initial_batch=4096, scale=0.0, max_batch=4096, reps=32, depth=2),
-    "b2048_r16": dict(initial_batch=2048, scale=0.0, max_batch=2048, reps=16, depth=2),
-    "b1024_r64": dict(initial_batch=1024, scale=0.0, max_batch=1024, reps=64, depth=2),
-    "b512_r8_serial": dict(initial_batch=512, scale=0.0, max_batch=512, reps=8, depth=1),
+    "uct_b2048_r16": dict(initial_batch=2048, scale=0.0, max_batch=2048, reps=16, depth=2, policy=1),
+    "uct_b8192_r8": dict(initial_batch=8192, scale=0.0, max_batch=8192, reps=8, depth=2, policy=1),
+    "uct_b16384_grow_2^18_r16": dict(initial_batch=16384, scale=0.02, max_batch=1 << 18, reps=16, depth=2, policy=1),
+    "uct_b512_r4": dict(initial_batch=512, scale=0.0, max_batch=512, reps=4, depth=2, policy=1),
+    "ref_b2048_r16": dict(initial_batch=2048, scale=0.0, max_batch=2048, reps=16, depth=2, policy=0),
 }
 
 
@@ -58,7 +57,8 @@ for name, cfg in CANDIDATES.items():
             else:
                 trees[turn].search_ex(eng, iterations=opp_trials // 50, initial_batch=50, scale=0.0, max_batch=50, reps=1, depth=1,
                                       threads=1, key=5000 * g + plies)
-            m = trees[turn].best_move(turn)
+            uct = seat[turn] == "cand" and cfg.get("policy") == 1
+            m = trees[turn].robust_move(turn) if uct else trees[turn].best_move(turn)
             for t in trees:
                 t.move(m)
             plies += 1
