@@ -621,13 +621,17 @@ def main():
         ndev = min(world, torch.cuda.device_count())
         seng = eng if ndev == 1 else b.Engine(devices=list(range(ndev)), seed=PLAY_KEY)
         rows = []
-        for batch, mx, sreps, depth in ((65536, 1 << 20, 32, 2), (65536, 1 << 20, 8, 2), (65536, 1 << 20, 256, 2), (65536, 1 << 20, 32, 1),
-                                        (4096, 4096, 32, 2)):
+        # allocation policy 0 = the reference's rule (GameTree::select), 1 = B2P_POLICY_UCT (what the B200 player uses)
+        for batch, mx, sreps, depth, policy in ((65536, 1 << 20, 32, 2, 0), (65536, 1 << 20, 8, 2, 0), (65536, 1 << 20, 256, 2, 0),
+                                                (65536, 1 << 20, 32, 1, 0), (4096, 4096, 32, 2, 0), (65536, 1 << 20, 32, 2, 1),
+                                                (2048, 2048, 16, 2, 1)):
             t = b.Tree(start)
-            t.search_ex(seng, iterations=3, initial_batch=batch, max_batch=mx, reps=sreps, key=1, depth=depth)   # warm-up
+            t.search_ex(seng, iterations=3, initial_batch=batch, max_batch=mx, reps=sreps, key=1, depth=depth, policy=policy)   # warm-up
             t = b.Tree(start)
-            st = t.search_ex(seng, seconds=args.search_seconds, initial_batch=batch, scale=0.02, max_batch=mx, reps=sreps, key=3, depth=depth)
+            st = t.search_ex(seng, seconds=args.search_seconds, initial_batch=batch, scale=0.02 if mx > batch else 0.0, max_batch=mx,
+                             reps=sreps, key=3, depth=depth, policy=policy)
             rows.append({"initial_batch": batch, "max_batch": mx, "reps_per_leaf": sreps, "depth": st["depth"], "host_threads": st["threads"],
+                         "policy": "uct" if policy else "reference",
                          "seconds": st["seconds"], "playouts_per_s": st["playouts"] / st["seconds"],
                          "leaf_selections_per_s": st["leaves"] / st["seconds"], "batches": st["batches"], "tree_nodes": st["nodes"],
                          "gpu_busy": st["kernel_s"] / st["seconds"], "select_s": st["select_s"], "update_s": st["update_s"],

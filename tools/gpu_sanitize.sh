@@ -13,8 +13,12 @@ for sched in (b.SCHED_THREAD, b.SCHED_WARP):
     e.run_packed(st, max_plies=7, sched=sched, want_final=True)
 e.genmoves(st, 48)
 t = b.Tree(st[5]); t.search(e, iterations=5, initial_batch=300, reps=4)
+t = b.Tree(st[7]); t.search_ex(e, iterations=6, initial_batch=3000, reps=4, depth=2, policy=1)
+from gpu_ai_b200 import engine as E
+e3 = b.Engine(devices=[0, 0, 0])
+s776 = E.unpack776(st); e3.run_states776(np.concatenate([s776] * 6)); e.run_states776(s776[:700], mode=b.MODE_HEURISTIC, sched=b.SCHED_AUTO)
 print("sanitizer workload done")
 PY
-for tool in memcheck racecheck synccheck; do
+for tool in ${SAN_TOOLS:-memcheck racecheck synccheck}; do
   echo "== $tool"; PYTHONPATH=$PWD timeout 900 compute-sanitizer --tool $tool --error-exitcode 9 python /tmp/san_workload.py > $OUT/sanitizer_$tool.txt 2>&1; echo "exit $?"; tail -3 $OUT/sanitizer_$tool.txt
 done
