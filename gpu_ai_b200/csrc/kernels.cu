@@ -31,7 +31,10 @@ namespace b2p {
 
 namespace {
 
-constexpr int kLaneBlock = 128;
+#ifndef B2P_LANE_BLOCK
+#define B2P_LANE_BLOCK 128  // 64 and 256 threads per block measured within noise of 128 (profiles/r02q_ab.txt)
+#endif
+constexpr int kLaneBlock = B2P_LANE_BLOCK;
 constexpr int kRatioA = 52, kRatioB = 49;  // material quotient table: numerator 0..51, denominator 0..48
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
@@ -68,7 +71,7 @@ __device__ __forceinline__ void fill_gauss_table(float2 *tab) {
 #define B2P_RAND_MIN_BLOCKS 1
 #endif
 template <int MODE, bool LIMITED>
-__global__ void __launch_bounds__(kLaneBlock, MODE == kHeuristic ? B2P_HEUR_MIN_BLOCKS : B2P_RAND_MIN_BLOCKS) playout_lanes_kernel(const PlayoutParams prm) {
+__global__ void __launch_bounds__(kLaneBlock, MODE == kHeuristic ? (B2P_HEUR_MIN_BLOCKS * 128) / kLaneBlock : B2P_RAND_MIN_BLOCKS) playout_lanes_kernel(const PlayoutParams prm) {
   constexpr bool kHeur = MODE == kHeuristic;
   constexpr bool kLeaf = MODE == kLeafGen;
   constexpr int kOrder = MODE == kRandomFast ? kOrderFast : kOrderCanonical;
