@@ -577,7 +577,7 @@ int b2p_run_counts(b2p_ctx *ctx, const b2p_state16 *states, size_t n, uint32_t r
 
 // Asynchronous form of b2p_run_counts for a pipelined caller (b2p_tree_search_ex): queues H2D copy, kernel and D2H
 // copy of the per-leaf counts on pipeline slot `slot` of every device the batch is sharded over and returns at once.
-int b2p_run_counts_async(b2p_ctx *ctx, int slot, const b2p_state16 *states, size_t n, uint32_t reps, uint64_t key,
+static int run_counts_async_impl(b2p_ctx *ctx, int slot, const b2p_state16 *states, size_t n, uint32_t reps, uint64_t key,
                          uint64_t pid_base, int mode, int sched, int order, uint32_t *wins_out) {
   if (!ctx) return B2P_EINVAL;
   if (slot < 0 || slot >= kSlots) return fail(ctx, B2P_EINVAL, "bad pipeline slot");
@@ -627,6 +627,24 @@ int b2p_run_counts_async(b2p_ctx *ctx, int slot, const b2p_state16 *states, size
     ctx->slot_span[slot] = g + 1;
   }
   return B2P_OK;
+}
+
+int b2p_run_counts_async(b2p_ctx *ctx, int slot, const b2p_state16 *states, size_t n, uint32_t reps, uint64_t key,
+                         uint64_t pid_base, int mode, int sched, int order, uint32_t *wins_out) {
+  if (ctx && slot >= 0 && slot < kSlots && ctx->slot_span[slot] != 0)
+    return fail(ctx, B2P_EINVAL, "pipeline slot still in flight: call b2p_wait_slot first");
+  const int rc = run_counts_async_impl(ctx, slot, states, n, reps, key, pid_base, mode, sched, order, wins_out);
+  if (rc != B2P_OK && ctx && slot >= 0 && slot < kSlots && ctx->slot_span[slot] != 0) {
+    // failed half-way through the devices: nothing of this batch may stay in flight, and the slot must be reusable
+    const std::string why = ctx->err;
+    for (int g = 0; g < ctx->slot_span[slot]; g++) {
+      Device &d = ctx->devs[g];
+      if (cudaSetDevice(d.id) == cudaSuccess) cudaStreamSynchronize(d.aux[slot] ? d.aux[slot] : d.stream);
+    }
+    ctx->slot_span[slot] = 0;
+    ctx->err = why;
+  }
+  return rc;
 }
 
 // Context-owned page-locked staging for a pipelined caller: room for `leaves` packed states and 2*`leaves` win
