@@ -418,12 +418,12 @@ struct b2p_tree {
   // sequential UCT search does with the same budget; the reference's rule above shares a batch out in proportion
   // to the UCB1 values, which are all of the same size (0.4 ... 1.5), i.e. almost uniformly -- with batches of
   // thousands of leaves it explores the first tree levels breadth-first however good or bad a move looks
-  // (measured: 300x the playouts of mcts_host buy a 57 % score, profiles/r02m_*).  Cost: trials x children
-  // comparisons per node, one weight update per trial.
+  // (measured: 300x the playouts of mcts_host buy a 57 % score, profiles/r02m_*).
   uint32_t distribute_uct(const Node &nd, uint32_t trials, uint32_t reps, uint32_t *child_trials) const {
     const uint32_t nc = nd.n_children, fc = nd.first_child;
-    float w[kMaxMoves], wins[kMaxMoves], tot[kMaxMoves];
-    const float two_log = 2.0f * logf((float)(nd.total > 1 ? nd.total : 2) + (float)trials * (float)reps);
+    double wins[kMaxMoves], tot[kMaxMoves], w[kMaxMoves];
+    const double L = 2.0 * std::log((double)(nd.total > 1 ? nd.total : 2) + (double)trials * (double)reps);
+    const double step = (double)reps;
     // a move is as good as the share of playouts through it that the player MAKING it wins.  (GameTree::ucb1,
     // src/mcts.cpp:182-191, reads wins[state.turn] of the CHILD -- the opponent's wins; under its near-uniform
     // allocation that hardly shows, and the serial interface reproduces it for parity.  Under UCT it would steer
@@ -431,20 +431,52 @@ struct b2p_tree {
     const unsigned mover = nd.state.meta & 1u;
     for (uint32_t i = 0; i < nc; i++) {
       const Node &c = at(fc + i);
-      wins[i] = (float)(int64_t)c.wins[mover];
-      tot[i] = (float)(int64_t)c.total;
-      w[i] = c.total == 0 ? INFINITY : wins[i] / tot[i] + sqrtf(two_log / tot[i]);
+      wins[i] = (double)c.wins[mover];
+      tot[i] = (double)c.total;
       child_trials[i] = 0;
     }
-    const float step = (float)reps;
-    for (uint32_t t = 0; t < trials; t++) {
+    uint32_t left = trials;
+    if (trials > 32 * nc) {
+      // Many trials: the one-by-one rule is a water-filling -- every child ends up with just enough visits M_i for
+      // its value W_i / M_i + sqrt(L / M_i) to sink to a common level lambda.  With y = 1 / sqrt(M) that is the
+      // quadratic W y^2 + sqrt(L) y = lambda, so the visits needed at a given level have a closed form; a bisection
+      // on lambda finds the highest level that fits the budget, the one-by-one loop below hands out the remainder.
+      const double sL = std::sqrt(L);
+      auto needed = [&](double lam, uint32_t *out) {
+        uint64_t sum = 0;
+        for (uint32_t i = 0; i < nc; i++) {
+          const double y = wins[i] > 0 ? (std::sqrt(L + 4.0 * wins[i] * lam) - sL) / (2.0 * wins[i]) : lam / sL;
+          const double m = 1.0 / (y * y);
+          double t = m > tot[i] ? std::ceil((m - tot[i]) / step) : 0.0;
+          if (t > (double)trials) t = (double)trials;
+          out[i] = (uint32_t)t;
+          sum += out[i];
+        }
+        return sum;
+      };
+      double lo = 0.0, hi = 1.0 + sL;  // at `hi` no child with a visit needs another one
+      uint32_t tmp[kMaxMoves];
+      for (int it = 0; it < 18; it++) {  // level to 2e-5: the loop below settles the rest
+        const double mid = 0.5 * (lo + hi);
+        if (needed(mid, tmp) > (uint64_t)trials) lo = mid;
+        else hi = mid;
+      }
+      if (needed(hi, tmp) <= (uint64_t)trials)
+        for (uint32_t i = 0; i < nc; i++) {
+          child_trials[i] = tmp[i];
+          tot[i] += step * (double)tmp[i];
+          left -= tmp[i];
+        }
+    }
+    for (uint32_t i = 0; i < nc; i++) w[i] = tot[i] == 0 ? INFINITY : wins[i] / tot[i] + std::sqrt(L / tot[i]);
+    for (; left > 0; left--) {
       uint32_t best = 0;
-      float bw = w[0];
+      double bw = w[0];
       for (uint32_t i = 1; i < nc; i++)
         if (w[i] > bw) { bw = w[i]; best = i; }
       child_trials[best]++;
       tot[best] += step;
-      w[best] = wins[best] / tot[best] + sqrtf(two_log / tot[best]);
+      w[best] = wins[best] / tot[best] + std::sqrt(L / tot[best]);
     }
     return trials;
   }
@@ -569,7 +601,7 @@ struct b2p_tree {
   // the first levels, on the calling thread: cuts the batch into items of at most `grain` trials
   void top_select(uint32_t id, uint32_t trials, uint32_t off, int depth, uint32_t grain, Batch &b, const SelCtx &c) {
     Node &nd = at(id);
-    if (trials <= grain || depth >= 5 || !descend(nd, trials, *c.cur)) {
+    if (trials <= grain || depth >= 48 || !descend(nd, trials, *c.cur)) {
       b.items.push_back({id, trials, off, 0u, 0u, 0u});
       return;
     }

@@ -194,6 +194,21 @@ class Engine:
         self._check(self.lib.b2p_run_counts(self.ctx, _ptr(a), n, reps, key, pid_base, mode, sched, order, _ptr(wins), _ptr(counters)))
         return wins, counters
 
+    def run_counts_async(self, slot, states, wins_out, reps, key=12345, pid_base=0, mode=MODE_RANDOM, sched=SCHED_THREAD,
+                         order=ORDER_FAST):
+        """b2p_run_counts_async: `states` (n, 4) uint32 and `wins_out` (n, 2) uint32 must stay alive (ideally
+        PinnedArray views) until wait_slot(slot) returns."""
+        n = states.shape[0]
+        self._check(self.lib.b2p_run_counts_async(self.ctx, slot, _ptr(states), n, reps, key, pid_base, mode, sched, order,
+                                                  _ptr(wins_out)))
+
+    def wait_slot(self, slot):
+        """returns (counters[4], kernel_ms)"""
+        counters = np.zeros(4, dtype=np.uint64)
+        ms = C.c_float()
+        self._check(self.lib.b2p_wait_slot(self.ctx, slot, _ptr(counters), C.byref(ms)))
+        return counters, float(ms.value)
+
     def genmoves(self, states, max_moves=64):
         a = _as_packed(states)
         n = a.shape[0]

@@ -394,6 +394,47 @@ def test_many_launches_in_flight_on_caller_streams(engine, port):
         assert np.array_equal(o.cpu().numpy(), expect[i % 3]), "launch %d" % i
 
 
+def test_async_count_slots_equal_the_blocking_call(engine):
+    """b2p_run_counts_async / b2p_wait_slot (what the pipelined search is built on): three batches in flight on three
+    slots from page-locked buffers give the counts of the blocking call; a busy slot refuses a second batch."""
+    import gpu_ai_b200 as b
+    from gpu_ai_b200.engine import PinnedArray
+    multi = b.Engine(devices=_multi_device_ids(), seed=1)
+    sizes = (30000, 777, 52001)
+    bufs = []
+    for slot, n in enumerate(sizes):
+        st = engine.gen_leaves(n, key=40 + slot)
+        ps, pw = PinnedArray((n, 4), np.uint32), PinnedArray((n, 2), np.uint32)
+        ps.array[:] = st
+        bufs.append((st, ps, pw))
+        multi.run_counts_async(slot, ps.array, pw.array, reps=5, key=9 + slot, pid_base=100 * slot)
+    with pytest.raises(b.B2PError, match="in flight"):
+        multi.run_counts_async(1, bufs[1][1].array, bufs[1][2].array, reps=5)
+    for slot in (2, 0, 1):
+        st, ps, pw = bufs[slot]
+        counters, kernel_ms = multi.wait_slot(slot)
+        wins, c = engine.run_counts(st, reps=5, key=9 + slot, pid_base=100 * slot)
+        assert np.array_equal(pw.array, wins) and np.array_equal(counters, c) and kernel_ms > 0
+    counters, kernel_ms = multi.wait_slot(3)        # idle slot: nothing to wait for
+    assert counters.sum() == 0 and kernel_ms == 0
+
+
+def test_uct_search_on_gpu(engine):
+    """B2P_POLICY_UCT through the pipelined search: deterministic, every playout accounted for, and it concentrates
+    its trials (the reference rule spreads them almost evenly over the root moves)."""
+    import gpu_ai_b200 as b
+    runs = []
+    for policy in (1, 1, 0):
+        t = b.Tree(START_PACKED)
+        st = t.search_ex(engine, iterations=40, initial_batch=2048, max_batch=2048, reps=8, key=5, depth=2, policy=policy)
+        mv, tr, w1, w2 = t.root_moves()
+        assert st["playouts"] == 40 * 2048 * 8 == tr.sum() == t.info()["total_trials"] and ((w1 + w2) <= tr).all()
+        runs.append(tr.copy())
+        assert t.robust_move(0) in set(int(x) for x in mv)
+    assert np.array_equal(runs[0], runs[1])
+    assert runs[0].max() / runs[0].sum() > runs[2].max() / runs[2].sum()
+
+
 def test_pinned_host_buffers(engine):
     import gpu_ai_b200 as b
     from gpu_ai_b200.engine import PinnedArray
