@@ -28,3 +28,21 @@ def test_our_arm_refuses_to_run_without_a_gpu():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0"], capture_output=True,
                        text=True, timeout=300, cwd=ROOT)
     assert r.returncode != 0 and "no CUDA device" in (r.stderr + r.stdout)
+
+
+def test_reference_arm_uses_all_cores_under_torchrun_env():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm sets its OpenMP thread count itself, reports it, and
+    says how many leaves a step plays (round-1 verdict: the N >= 2 ratios were taken against a 1-thread arm)."""
+    env = dict(os.environ, OMP_NUM_THREADS="1", RANK="0", WORLD_SIZE="2", LOCAL_RANK="0")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0",
+                        "--ref-seconds", "0.3"], capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][0])
+    cpus = len(os.sched_getaffinity(0))
+    assert d["cpu_baseline"]["cores"] == cpus == d["config"]["omp_threads"] and d["n_gpus"] == 2
+    assert d["config"]["leaves_per_step"] > 0 and d["config"]["playouts_per_step"] == d["config"]["leaves_per_step"]
+    # the other ranks print nothing and exit 0
+    env["RANK"] = "1"
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+    assert r.returncode == 0 and not [l for l in r.stdout.splitlines() if l.startswith("{")]
