@@ -6,6 +6,8 @@
 //   mode hybrid  side A = the reference's `mcts_hybrid` preset (MCTSPlayer(50, 0.02, T, HybridPlayoutDriver(1.2)),
 //                src/player.cpp:173-175) running on the drop-in (shim/playout_shim.cpp + shim/hybrid_b200.cpp)
 //   mode device  side A = the reference's `mcts_device_multiple` preset (MCTSPlayer(50, 0.02, T, DeviceMultiple...))
+//   mode optimal side A = the reference's `mcts_optimal` preset (MCTSPlayer(50, 0.004, T, OptimalPlayoutDriver), its bandit
+//                over {host, device_multiple, hybrid(host, device_coarse)} unchanged, src/playout.cpp:85-172)
 //   side B is always the reference's `mcts_host` preset (MCTSPlayer(50, 0, T, HostPlayoutDriver), src/player.cpp:164-166).
 // The presets' 7-second move time (an `unsigned` number of seconds slept in getMove, src/player.cpp:99) is replaced
 // by the command-line budgets; everything else -- tree, pondering worker thread, playout drivers -- is the
@@ -133,7 +135,7 @@ int main(int argc, char **argv) {
   const float scale = argc > 7 ? (float)std::atof(argv[7]) : 0.0f;
   const int policy = argc > 8 ? std::atoi(argv[8]) : B2P_POLICY_UCT;  // 0 = the reference's allocation rule
   int score[3] = {0, 0, 0};  // A wins, mcts_host wins, draws
-  const char *name_a = mode == "b200" ? "b200_tree" : mode == "hybrid" ? "mcts_hybrid(drop-in)" : "mcts_device_multiple(drop-in)";
+  const char *name_a = mode == "b200" ? "b200_tree" : mode == "hybrid" ? "mcts_hybrid(drop-in)" : mode == "optimal" ? "mcts_optimal(drop-in)" : "mcts_device_multiple(drop-in)";
   for (int g = 0; g < games; g++) {
     B200TreePlayer *mine = nullptr;
     std::unique_ptr<Player> players[NUM_PLAYERS];
@@ -143,6 +145,8 @@ int main(int argc, char **argv) {
       players[seat_a] = std::unique_ptr<Player>(mine);
     } else if (mode == "hybrid") {
       players[seat_a] = std::make_unique<MCTSPlayer>(50, 0.02f, (unsigned)seconds_a, std::make_unique<HybridPlayoutDriver>(1.2f));
+    } else if (mode == "optimal") {
+      players[seat_a] = std::make_unique<MCTSPlayer>(50, 0.004f, (unsigned)seconds_a, std::make_unique<OptimalPlayoutDriver>());
     } else {
       players[seat_a] = std::make_unique<MCTSPlayer>(50, 0.02f, (unsigned)seconds_a, std::make_unique<DeviceMultiplePlayoutDriver>());
     }

@@ -15,6 +15,8 @@
 #include "playout.hpp"       // reference: src/playout.hpp
 #include "genMovesTest.hpp"  // reference: src/genMovesTest.hpp
 
+#include <atomic>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
@@ -50,8 +52,29 @@ b2p_ctx *context() {
   return tc.ctx;
 }
 
-std::vector<PlayerId> run(const std::vector<State> &states, int mode, int sched) {
+// calls and playouts per device driver, printed at exit when B2P_ROUTING_REPORT is set (with the counters of the
+// re-tuned hybrid drivers in hybrid_b200.cpp): shows where OptimalPlayoutDriver's bandit and the MCTS players send
+// their batches
+struct DriverCount {
+  const char *name;
+  std::atomic<unsigned long> calls{0}, playouts{0};
+};
+DriverCount g_counts[4] = {{"device_single"}, {"device_coarse"}, {"device_multiple"}, {"device_heuristic"}};
+
+void report_device_calls() {
+  if (!std::getenv("B2P_ROUTING_REPORT")) return;
+  for (DriverCount &c : g_counts)
+    if (c.calls.load())
+      std::fprintf(stderr, "{\"b2p_device_driver\": \"%s\", \"calls\": %lu, \"playouts\": %lu}\n", c.name, c.calls.load(), c.playouts.load());
+}
+struct CountRegistrar {
+  CountRegistrar() { std::atexit(report_device_calls); }
+} g_count_registrar;
+
+std::vector<PlayerId> run(const std::vector<State> &states, int mode, int sched, int which) {
   std::vector<PlayerId> results(states.size());
+  g_counts[which].calls++;
+  g_counts[which].playouts += states.size();
   if (states.empty()) return results;  // src/singlePlayout.cu:73-75
   b2p_ctx *ctx = context();
   if (b2p_run_states776(ctx, states.data(), states.size(), mode, sched, reinterpret_cast<int32_t *>(results.data())) != B2P_OK)
@@ -61,10 +84,10 @@ std::vector<PlayerId> run(const std::vector<State> &states, int mode, int sched)
 
 }  // namespace
 
-std::vector<PlayerId> DeviceSinglePlayoutDriver::runPlayouts(std::vector<State> states) { return run(states, B2P_MODE_RANDOM, B2P_SCHED_THREAD); }
-std::vector<PlayerId> DeviceCoarsePlayoutDriver::runPlayouts(std::vector<State> states) { return run(states, B2P_MODE_RANDOM, B2P_SCHED_THREAD); }
-std::vector<PlayerId> DeviceMultiplePlayoutDriver::runPlayouts(std::vector<State> states) { return run(states, B2P_MODE_RANDOM, B2P_SCHED_AUTO); }
-std::vector<PlayerId> DeviceHeuristicPlayoutDriver::runPlayouts(std::vector<State> states) { return run(states, B2P_MODE_HEURISTIC, B2P_SCHED_AUTO); }
+std::vector<PlayerId> DeviceSinglePlayoutDriver::runPlayouts(std::vector<State> states) { return run(states, B2P_MODE_RANDOM, B2P_SCHED_THREAD, 0); }
+std::vector<PlayerId> DeviceCoarsePlayoutDriver::runPlayouts(std::vector<State> states) { return run(states, B2P_MODE_RANDOM, B2P_SCHED_THREAD, 1); }
+std::vector<PlayerId> DeviceMultiplePlayoutDriver::runPlayouts(std::vector<State> states) { return run(states, B2P_MODE_RANDOM, B2P_SCHED_AUTO, 2); }
+std::vector<PlayerId> DeviceHeuristicPlayoutDriver::runPlayouts(std::vector<State> states) { return run(states, B2P_MODE_HEURISTIC, B2P_SCHED_AUTO, 3); }
 
 // Device move list vs host State::genMoves, element-wise Move::operator== (src/state.cu:440-454),
 // same contract and same diagnostics as the reference's genMovesTest.
