@@ -40,9 +40,11 @@ void pack_scalar(const unsigned char *s, size_t n, b2p_state16 *out) {
         uint32_t owner;
         std::memcpy(&w, q, 8);
         std::memcpy(&owner, q + 8, 4);
-        const uint32_t oc = (uint32_t)(w & 0xFFu) != 0u;  // BoardItem::occupied
-        const uint32_t ty = (uint32_t)(w >> 32) == 1u;    // CHECKER_KING
-        const uint32_t ow = owner != 0u;                  // PLAYER_2
+        // the LOW BYTE of each field decides, in both implementations (the enums only take the values 0 and 1
+        // where a piece stands): any byte pattern packs to the same bits on either path
+        const uint32_t oc = (uint32_t)(w & 0xFFu) != 0u;          // BoardItem::occupied
+        const uint32_t ty = (uint32_t)((w >> 32) & 0xFFu) != 0u;  // CHECKER_KING = 1
+        const uint32_t ow = (owner & 0xFFu) != 0u;                // PLAYER_2 = 1
         const int sq = r * 4 + j;
         occ |= oc << sq;
         p2 |= (oc & ow) << sq;

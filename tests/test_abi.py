@@ -77,15 +77,24 @@ for byte in (1, 2, 3):
     board[:, :, byte] = rng.integers(0, 256, size=occ.shape).astype(np.uint8)
 out = engine.pack776(s)
 assert np.array_equal(out, leaves), "packer mismatch"
+# arbitrary bytes (not valid States): both implementations are defined on the low byte of every field, so the
+# digest of the packed output must not depend on which one ran
+fuzz = np.random.default_rng(7).integers(0, 256, size=(20000, 776), dtype=np.uint8)
+fuzz[:, ::3] &= np.random.default_rng(8).integers(0, 2, size=fuzz[:, ::3].shape, dtype=np.uint8) * 255
+digest = int(engine.pack776(fuzz).astype(np.uint64).sum())
+print(digest)
 print(b.load_library().b2p_pack776_impl().decode())
 """ % (ROOT, os.path.join(ROOT, "tests", "golden", "reference_vectors.npz"))
-    seen = set()
+    seen, digests = set(), set()
     for force in ("0", "1"):
         r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, B2P_PACK_SCALAR=force), stdout=subprocess.PIPE,
                            stderr=subprocess.PIPE, text=True, timeout=300)
         assert r.returncode == 0, r.stderr[-2000:]
-        seen.add(r.stdout.strip().splitlines()[-1])
+        lines = r.stdout.strip().splitlines()
+        seen.add(lines[-1])
+        digests.add(lines[-2])
     assert "scalar" in seen and seen <= {"scalar", "avx512bw+bmi2"}
+    assert len(digests) == 1
 
 
 def test_expand_move_matches_reference_move_layout(lib, golden):
