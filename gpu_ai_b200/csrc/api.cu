@@ -785,7 +785,8 @@ int b2p_run_states776(b2p_ctx *ctx, const void *states, size_t n, int mode, int 
       if (e != cudaSuccess) err = std::string("b2p_run_states776 pipeline: ") + cudaGetErrorString(e);
     }
   };
-  ctx->pool.run(tasks.size(), worker);
+  // at most 32 packers per context: the loop is bound by host memory bandwidth, and one process per GPU may run it
+  ctx->pool.run(std::min<size_t>(tasks.size(), 32), worker);
   // wait for every stream that may carry work of this call -- also on the error path: the next call may
   // grow (free + reallocate) buffers that kernels still in flight are writing
   cudaError_t sync_err = cudaSuccess;
@@ -817,7 +818,7 @@ int b2p_run_states776(b2p_ctx *ctx, const void *states, size_t n, int mode, int 
       }
     }
   };
-  ctx->pool.run(blocks, widen);
+  ctx->pool.run(std::min<size_t>(blocks, 32), widen);
   return B2P_OK;
 }
 

@@ -26,7 +26,7 @@ class Pool {
   // runs f() on `workers` threads in total (the caller is one of them); returns when all have returned
   void run(size_t workers, const std::function<void()> &f) {
     const unsigned hw = std::thread::hardware_concurrency();
-    const size_t cap = std::min<size_t>(hw ? hw : 1, 32);
+    const size_t cap = std::min<size_t>(hw ? hw : 1, 64);
     workers = std::min(workers, cap);
     if (workers <= 1) {
       f();

@@ -904,7 +904,7 @@ int b2p_tree_search_ex(b2p_ctx *ctx, b2p_tree *t, const b2p_search_opts *o, b2p_
     return B2P_OK;
   }
   const unsigned hw = std::thread::hardware_concurrency();
-  const size_t threads = o->threads > 0 ? (size_t)o->threads : std::max<size_t>(1, std::min<size_t>(hw ? hw : 1, 32));
+  const size_t threads = o->threads > 0 ? (size_t)o->threads : std::max<size_t>(1, std::min<size_t>(hw ? hw : 1, 64));
   const int depth = o->depth <= 0 ? 2 : std::min(o->depth, kPipeSlots);
   // one launch holds fewer than 2^31 playouts per device; a batch also never exceeds max_batch leaves
   uint64_t cap = o->max_batch ? o->max_batch : (1u << 20);

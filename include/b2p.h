@@ -234,7 +234,7 @@ typedef struct b2p_search_opts {
   uint32_t reps;          /* playouts per selected leaf */
   int mode;               /* B2P_MODE_* */
   uint64_t key;           /* Philox key of round r = key + r; playout ids count up over the whole search */
-  int threads;            /* host threads for select/update; 0 = min(hardware threads, 32) */
+  int threads;            /* host threads for select/update; 0 = min(hardware threads, 64) */
   int depth;              /* batches in flight: 1 serial, 2..4 pipelined; 0 = 2 */
   int policy;             /* B2P_POLICY_*: how a node hands its trials to its children */
 } b2p_search_opts;
