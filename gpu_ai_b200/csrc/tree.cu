@@ -674,7 +674,7 @@ struct b2p_tree {
         const Visit *vs = lists[it.worker].visits[b.slot].data() + it.vbegin;
         const size_t nv = it.vend - it.vbegin;
         for (size_t v = 0; v < nv; v++) {
-          if (v + 8 < nv) __builtin_prefetch(&at(vs[v + 8].node), 1);
+          if (v + 24 < nv) __builtin_prefetch(&at(vs[v + 24].node), 1);
           const Visit &vi = vs[v];
           Node &nd = at(vi.node);
           nd.wins[0] += pre1[vi.end - 1] - (vi.begin > it.off ? pre1[vi.begin - 1] : 0u);
