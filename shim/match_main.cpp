@@ -18,6 +18,10 @@
 #include "playout.hpp"  // reference
 #include "state.hpp"    // reference
 
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
+
 #include <chrono>
 #include <cmath>
 #include <cstdlib>
@@ -124,7 +128,19 @@ Move verbose_move(Player &p, const State &s, uint64_t &tree_size_sum, uint64_t &
 
 }  // namespace
 
+// a crash in a tournament that runs for an hour should say where
+static void on_crash(int sig) {
+  void *frames[64];
+  const int n = backtrace(frames, 64);
+  const char msg[] = "match_b200: fatal signal, backtrace:\n";
+  (void)!write(2, msg, sizeof msg - 1);
+  backtrace_symbols_fd(frames, n, 2);
+  _exit(128 + sig);
+}
+
 int main(int argc, char **argv) {
+  signal(SIGSEGV, on_crash);
+  signal(SIGABRT, on_crash);
   const std::string mode = argc > 1 ? argv[1] : "b200";
   const int games = argc > 2 ? std::atoi(argv[2]) : 2;
   const double seconds_a = argc > 3 ? std::atof(argv[3]) : 1.0;
