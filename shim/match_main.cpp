@@ -150,6 +150,24 @@ int main(int argc, char **argv) {
   const uint32_t batch = argc > 5 ? (uint32_t)std::atoi(argv[5]) : 2048, reps = argc > 6 ? (uint32_t)std::atoi(argv[6]) : 16;
   const float scale = argc > 7 ? (float)std::atof(argv[7]) : 0.0f;
   const int policy = argc > 8 ? std::atoi(argv[8]) : B2P_POLICY_UCT;  // 0 = the reference's allocation rule
+  {
+    // Create the process's CUDA context and load the kernels BEFORE any game clock starts.  The reference's players
+    // move after a fixed sleep whatever their worker thread has achieved; with 1-second moves the very first device
+    // batch (context creation + module load, about a second in a fresh process) may not be back yet, every root
+    // child then has 0 trials, GameTree::getOptMove compares NaN scores, returns an indeterminate Move
+    // (src/mcts.cpp:39-55, its assert is compiled out), GameTree::move finds no such child and returns a null tree
+    // (src/mcts.cpp:11-25), and the next getMove dereferences it.  (Seen as a segfault in State::operator== at
+    // the second move of `mcts_device_multiple` games; the reference's own 7-second moves hide it.)
+    b2p_ctx *warm = nullptr;
+    if (b2p_create(&warm, nullptr, 0, 1) != B2P_OK) throw std::runtime_error(b2p_last_error(nullptr));
+    State s0 = getStartingState();
+    b2p_state16 packed;
+    b2p_pack776(&s0, 1, &packed);
+    for (int mode_i : {B2P_MODE_RANDOM, B2P_MODE_HEURISTIC})
+      for (int sched : {B2P_SCHED_THREAD, B2P_SCHED_WARP})  // lazy module loading: touch every kernel the drivers use
+        b2p_run_packed(warm, &packed, 1, 8, 1, 0, mode_i, sched, B2P_ORDER_FAST, -1, nullptr, nullptr, nullptr, nullptr);
+    b2p_destroy(warm);
+  }
   int score[3] = {0, 0, 0};  // A wins, mcts_host wins, draws
   const char *name_a = mode == "b200" ? "b200_tree" : mode == "hybrid" ? "mcts_hybrid(drop-in)" : mode == "optimal" ? "mcts_optimal(drop-in)" : "mcts_device_multiple(drop-in)";
   for (int g = 0; g < games; g++) {
