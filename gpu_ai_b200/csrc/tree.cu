@@ -698,6 +698,13 @@ struct b2p_tree {
       nd.wins[0] += base1[hi] - base1[lo];
       nd.wins[1] += base2[hi] - base2[lo];
     }
+    b.n = 0;  // folded in: the slot is free, and b2p_tree_move may re-root again
+  }
+
+  bool batches_pending() const {
+    for (const Batch &b : batch)
+      if (b.n != 0) return true;
+    return false;
   }
 };
 
@@ -795,6 +802,11 @@ int b2p_tree_robust_move(const b2p_tree *t, int player, b2p_move_t *move_out) {
 // rest of the old tree is freed), or start a new tree from the successor state when the root was never expanded.
 int b2p_tree_move(b2p_tree *t, b2p_move_t move) {
   if (!t) return B2P_EINVAL;
+  if (t->batches_pending()) {
+    // the visit records of a selected batch name nodes of the arena this call is about to free
+    t->err = "b2p_tree_move: a batch selected with b2p_tree_select_batch has not been folded in (b2p_tree_update_batch) yet";
+    return B2P_EINVAL;
+  }
   const Node &r = t->at(t->root);
   b2p_move_t buf[kMaxMoves];
   const int n_moves = t->root_move_list(buf);
@@ -885,7 +897,6 @@ int b2p_tree_update_batch(b2p_tree *t, int slot, const uint32_t *wins, int threa
   if (!t || slot < 0 || slot >= kPipeSlots) return B2P_EINVAL;
   if (t->batch[slot].n && !wins) return B2P_EINVAL;
   t->update_batch(t->batch[slot], wins, (size_t)std::max(1, threads));
-  t->batch[slot].n = 0;
   return B2P_OK;
 }
 
@@ -941,9 +952,10 @@ int b2p_tree_search_ex(b2p_ctx *ctx, b2p_tree *t, const b2p_search_opts *o, b2p_
       t->err = std::string("b2p_tree_search: ") + b2p_last_error(ctx);
       return r;
     }
+    const uint64_t leaves_in_batch = b.n;
     t->update_batch(b, t->h_wins[slot], threads);
     st.update_s += now_s() - w1;
-    st.playouts += (uint64_t)b.n * o->reps;
+    st.playouts += leaves_in_batch * o->reps;
     retired++;
     return B2P_OK;
   };

@@ -250,7 +250,8 @@ typedef struct b2p_search_stats {
  * as `reps` trials each and remembers the batch in `slot` (0..3); policy 0 = the reference's rule with the reference's
  * expression types (bit-identical decisions, what depth 1 uses), 1 = the same rule in single precision (what
  * depth >= 2 uses), 2 = B2P_POLICY_UCT; update_batch folds the batch's per-leaf win counts
- * (b2p_run_counts layout) into the nodes it visited.  Several slots may be selected before the first is updated. */
+ * (b2p_run_counts layout) into the nodes it visited.  Several slots may be selected before the first is updated;
+ * b2p_tree_move refuses to re-root while a selected batch has not been folded in. */
 int b2p_tree_select_batch(b2p_tree *tree, int slot, uint32_t trials, uint32_t reps, int threads, int policy,
                           b2p_state16 *leaves_out);
 int b2p_tree_update_batch(b2p_tree *tree, int slot, const uint32_t *wins, int threads);

@@ -262,3 +262,19 @@ def test_uct_policy_is_consistent_deterministic_and_stronger(port):
                 tr_.move(m)
             plies += 1
     assert points >= 4.5, points
+
+
+def test_rerooting_is_refused_while_a_batch_is_outstanding():
+    """the visit records of a selected batch name nodes of the arena that b2p_tree_move frees"""
+    import gpu_ai_b200 as b
+    t = b.Tree(START_PACKED)
+    first = t.select_batch(0, 500, reps=2, threads=2)
+    t.update_batch(0, fake_counts(first, 2, 1), threads=2)
+    pend = t.select_batch(1, 64, reps=2, threads=1)
+    mv, tr, _, _ = t.root_moves()
+    with pytest.raises(b.B2PError, match="not been folded in"):
+        t.move(int(mv[0]))
+    t.update_batch(1, fake_counts(pend, 2, 99), threads=1)
+    mv, tr, _, _ = t.root_moves()
+    t.move(int(mv[0]))
+    assert t.info()["total_trials"] == int(tr[0])
